@@ -1,0 +1,419 @@
+"""``qse_b200.B200`` — the B200-native state-vector Calculator (drop-in beside ``qse.calc.Qutip``).
+
+Mirrors the reference plugin protocol (ICHEC/qse 1.1.21):
+
+* constructor ``(qbits, amplitude, detuning)`` in Qutip's positional order, bare ``Signal``
+  wrapped into ``Signals([signal])``, ``_check_pulses`` rules and messages
+  (qse/calc/qutip.py:13-32, 75-88); ``qbits`` may be ``None`` and attached later as with
+  ``Pulser`` (qse/calc/pulser.py:95-135); availability gate through
+  ``Calculator.__init__(qbits, label, is_calculator_available, installation_message)``
+  (qse/calc/calculator.py:86-101): a missing library / GPU raises ``Exception(message)``.
+* ``calculate(e_ops=None)`` runs the loop of qse/calc/qutip.py:34-53 on the GPU and BOTH returns
+  Qutip's dict ``{"state": (2^N, 1) complex128[, "expectations": (n_steps, n_ops)]}`` AND sets
+  ``results`` / ``statevector`` / ``spins`` the way Pulser and Myqlm do
+  (qse/calc/pulser.py:194-204) so the base-class getters work.
+* ``get_spins`` / ``get_sij`` / ``structure_factor_from_sij`` override the base-class versions
+  (qse/calc/calculator.py:125-187), which call the O(4^N) Python loops of qse/magnetic.py.
+* ``get_hamiltonian(amp, det)`` returns a handle usable as an ``e_op`` (the notebook idiom of
+  docs/use-cases/adiabatic.ipynb cell 6) instead of a QuTiP ``Qobj``.
+
+Sharded (multi-GPU) use is SPMD: one process per GPU under ``torchrun``; every rank builds
+the same calculator and calls the same methods; ``torch.distributed`` only carries the
+bootstrap (NCCL id) and optional state gathers — the exchange of sharded qubits lives in
+libqsb (peer memory over NVLink, NCCL for the scalar reductions).
+"""
+
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import host, lib
+
+try:  # a real install of the reference: be a true subclass of its plugin base class
+    from qse.calc.calculator import Calculator as _ReferenceCalculator  # type: ignore
+except Exception:  # the GPU boxes: no qse / QuTiP / matplotlib
+    _ReferenceCalculator = None
+
+C6 = host.C6
+
+INSTALLATION_MESSAGE = (
+    "The B200 calculator needs libqsb.so (build: python -m qse_b200._build) and an sm_100 "
+    "CUDA device; there is no CPU fallback."
+)
+
+
+class _MirrorCalculator:
+    """Stand-in for qse.calc.calculator.Calculator (qse/calc/calculator.py:70-187)."""
+
+    def __init__(self, qbits, label: str, is_calculator_available: bool, installation_message: str):
+        if not is_calculator_available:
+            raise Exception(installation_message)
+        self._qbits = qbits
+        self._label = label
+        self.spins = None
+        self.sij = None
+
+    @property
+    def label(self):
+        return self._label
+
+    @label.setter
+    def label(self, label):
+        self._label = label
+
+    @property
+    def qbits(self):
+        return self._qbits
+
+    @qbits.setter
+    def qbits(self, qbits):
+        self._qbits = qbits
+
+    def calculate(self):
+        raise NotImplementedError
+
+
+_Base = _ReferenceCalculator or _MirrorCalculator
+
+
+class Hamiltonian:
+    """Handle for H(amplitude, detuning) of one calculator — what ``get_hamiltonian`` returns.
+
+    Usable in ``calculate(e_ops=[...])`` (expectation of H after every step); ``diagonal()`` and
+    ``apply(psi)`` give access to the matrix-free operator on the device.
+    """
+
+    def __init__(self, calc: "B200", amplitude: float, detuning: float):
+        self.calc = calc
+        self.amplitude = float(amplitude)
+        self.detuning = float(detuning)
+
+    def diagonal(self) -> np.ndarray:
+        """diag(H) of this rank's shard: E_int[k] - detuning * popcount(k)."""
+        eng = self.calc._engine_ready()
+        k = np.arange(eng.local_dim, dtype=np.uint64) + np.uint64(eng.rank * eng.local_dim)
+        pop = np.zeros(eng.local_dim, dtype=np.int64)
+        for b in range(self.calc._nqbits()):
+            pop += ((k >> np.uint64(b)) & np.uint64(1)).astype(np.int64)
+        return self.detuning * (-1.0 * pop) + eng.diagonal()
+
+    def apply(self, psi) -> np.ndarray:
+        eng = self.calc._engine_ready()
+        eng.set_state(np.asarray(psi, dtype=np.complex128).reshape(-1))
+        return eng.apply_h(self.amplitude, self.detuning)
+
+    def __repr__(self):
+        return f"Hamiltonian(amplitude={self.amplitude}, detuning={self.detuning})"
+
+
+def _as_signals(pulse):
+    if pulse is None:
+        return None
+    if host._is_signals(pulse):
+        return pulse
+    return host.Signals([pulse])
+
+
+def _check_pulses(amplitude, detuning):
+    """qse/calc/qutip.py:75-88 — same rules, same messages."""
+    if amplitude.duration != detuning.duration:
+        raise Exception("The amplitude and detuning must have the same duration.")
+    if len(amplitude) != len(detuning):
+        raise Exception("The amplitude and detuning must contain the same number of signals.")
+    for a, d in zip(amplitude, detuning):
+        if len(a) != len(d):
+            raise Exception("The amplitude and detuning must have the same amount of values.")
+
+
+def _nano_to_micro(t):
+    return t / 1000
+
+
+def interaction_matrix(positions, c6: float = C6, tol: float = 1e-8) -> np.ndarray:
+    """V[i, j] (i<j) = c6 / |R_i - R_j|**6, kept iff |V| > tol.
+
+    The host keeps the reference's exact expression — ``lambda d: self.c6 / d**6``
+    (qse/calc/qutip.py:61-63) through the pair loop and cut-off of qse/qbits.py:1296-1304 with
+    the distance of qse/qbits.py:1008 — so the coefficients are bit-identical; only the
+    expansion to the 2^N diagonal happens on the GPU (qsb_set_interaction).
+    """
+    positions = np.asarray(positions, dtype=float)
+    n = positions.shape[0]
+    v = np.zeros((n, n), dtype=np.float64)
+    for i in range(n - 1):
+        for j in range(i + 1, n):
+            coef = c6 / np.linalg.norm(positions[i] - positions[j]) ** 6
+            if np.abs(coef) > tol:
+                v[i, j] = coef
+    return v
+
+
+def flatten_schedule(amplitude, detuning):
+    """(omega[], delta[], dt_us[]) per signal value, in the order of qse/calc/qutip.py:40-42.
+
+    dt is taken from the AMPLITUDE segment only (``amp_s.time_per_value()``, :41).
+    """
+    om, de, dt = [], [], []
+    for amp_s, det_s in zip(amplitude, detuning):
+        step = _nano_to_micro(amp_s.time_per_value())
+        for a, d in zip(amp_s.values, det_s.values):
+            om.append(float(a))
+            de.append(float(d))
+            dt.append(step)
+    return (np.array(om, dtype=np.float64), np.array(de, dtype=np.float64), np.array(dt, dtype=np.float64))
+
+
+def _pauli_masks(operator, indices, nqbits):
+    """(xmask, ymask, zmask, nmask) of one Pauli string; qubit q <-> bit N-1-q."""
+    masks = {"X": 0, "Y": 0, "Z": 0, "N": 0}
+    seen = 0
+    for op, q in zip(operator, indices):
+        if op not in masks:
+            raise Exception("An operator must be one of 'X', 'Y', 'Z' or 'N'.")
+        bit = 1 << (nqbits - 1 - int(q))
+        if seen & bit:
+            raise Exception("A qubit may appear only once in an operator string.")
+        seen |= bit
+        masks[op] |= bit
+    return masks["X"], masks["Y"], masks["Z"], masks["N"]
+
+
+class B200(_Base):
+    """B200-native state-vector calculator for the Rydberg Hamiltonian
+
+        H = (Omega/2) sum_i X_i - delta sum_i n_i + sum_{i<j} C6/|R_i-R_j|^6 n_i n_j .
+
+    Parameters
+    ----------
+    qbits : qse.Qbits | qse_b200.Qbits | None
+        Anything with ``positions`` (N x d) and ``nqbits``; may be attached later.
+    amplitude, detuning : Signal | Signals
+        Piecewise-constant pulses (ns; values in rad/us).
+    device : int, optional
+        CUDA device (default: ``LOCAL_RANK`` under torchrun, else 0).
+    method : {"taylor", "rk4"}
+        "taylor": norm-terminated Taylor propagator of each segment (exact to ``tol``);
+        "rk4": its 4-term truncation (classical RK4, one H psi chain per segment).
+    tol : float
+        Termination threshold on the norm of a Taylor term (default 1e-14).
+    distributed : bool | None
+        Shard over ``torch.distributed`` ranks; ``None`` = when a process group is up.
+    return_state : bool
+        ``False`` keeps the final state on the device (needed from ~28 qubits up).
+    wtimes : bool
+        Print wall-clock timings like the Pulser / Myqlm calculators do.
+    """
+
+    c6 = C6  # qse/calc/qutip.py:7, 11
+
+    def __init__(self, qbits=None, amplitude=None, detuning=None, *, device=None, method="taylor", tol=1e-14,
+                 distributed=None, return_state=True, compute_spins=True, wtimes=False, label="b200"):
+        ok, why = lib.is_available()
+        super().__init__(qbits=qbits, label=label, is_calculator_available=ok,
+                         installation_message=INSTALLATION_MESSAGE + (" (" + why + ")" if why else ""))
+        amplitude = _as_signals(amplitude)
+        detuning = _as_signals(detuning)
+        if amplitude is not None and detuning is not None:
+            _check_pulses(amplitude, detuning)
+        self.amplitude = amplitude
+        self.detuning = detuning
+        if method not in ("taylor", "rk4"):
+            raise ValueError("method must be 'taylor' or 'rk4'")
+        self.method = method
+        self.tol = float(tol)
+        self.device = device
+        self.distributed = distributed
+        self.return_state = return_state
+        self.compute_spins = compute_spins
+        self.wtimes = wtimes
+        self.results = None
+        self.metrics = None
+        self._statevector = None
+        self._engine = None
+        self._engine_key = None
+
+    # ---- attachment --------------------------------------------------------------------
+    def set_qbits(self, qbits):
+        """Hook called by ``Qbits(calculator=...)`` / ``qbits.calc = calc`` (qse/qbits.py:169-173)."""
+        self._qbits = qbits
+
+    def _nqbits(self) -> int:
+        if self.qbits is None:
+            raise Exception("No qbits attached to the calculator.")
+        return int(self.qbits.nqbits)
+
+    # ---- engine life cycle ---------------------------------------------------------------
+    def _comm(self):
+        """(rank, world, device) of this process."""
+        rank, world = 0, 1
+        use = self.distributed
+        if use is None or use:
+            try:
+                import torch.distributed as dist
+
+                if dist.is_available() and dist.is_initialized():
+                    rank, world = dist.get_rank(), dist.get_world_size()
+            except ImportError:
+                pass
+        if use and world == 1:
+            raise Exception("distributed=True needs an initialised torch.distributed process group")
+        if use is False:
+            rank, world = 0, 1
+        device = self.device
+        if device is None:
+            import os
+
+            device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else 0
+        return rank, world, device
+
+    def _engine_ready(self) -> lib.Engine:
+        """(Re)build the device context when the register changed (the reference goes stale)."""
+        n = self._nqbits()
+        positions = np.array(self.qbits.positions, dtype=float)
+        key = (n, positions.tobytes(), float(self.c6))
+        if self._engine is not None and self._engine_key == key:
+            return self._engine
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+        rank, world, device = self._comm()
+        uid = None
+        if world > 1:
+            from . import distributed as qdist
+
+            uid = qdist.broadcast_unique_id()
+        eng = lib.Engine(n, device=device, rank=rank, nranks=world, nccl_uid=uid)
+        eng.set_interaction(interaction_matrix(positions, self.c6))
+        self._engine = eng
+        self._engine_key = key
+        self._statevector = None
+        self.results = None
+        return eng
+
+    def close(self):
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+            self._engine_key = None
+
+    # ---- the hot path ---------------------------------------------------------------------
+    def get_hamiltonian(self, amplitude, detuning) -> Hamiltonian:
+        """H(amplitude, detuning) as an e_op handle (reference: a Qobj, qse/calc/qutip.py:55-58)."""
+        return Hamiltonian(self, amplitude, detuning)
+
+    def _pack_eops(self, e_ops):
+        n = self._nqbits()
+        packed = []
+        for op in e_ops:
+            if isinstance(op, Hamiltonian):
+                packed.append(("energy", op.amplitude, op.detuning))
+            elif isinstance(op, tuple) and len(op) == 3 and op[0] in ("H", "energy"):
+                packed.append(("energy", float(op[1]), float(op[2])))
+            elif hasattr(op, "operator_list"):  # qse.Operators
+                packed.append(("pauli", [(float(t.coef), *_pauli_masks(t.operator, t.indices, n))
+                                         for t in op.operator_list]))
+            elif hasattr(op, "operator") and hasattr(op, "indices"):  # qse.Operator
+                packed.append(("pauli", [(float(op.coef), *_pauli_masks(op.operator, op.indices, n))]))
+            else:
+                raise TypeError("e_ops entries must be calc.get_hamiltonian(amp, det), ('H', amp, det), "
+                                "or qse.Operator / qse.Operators with X/Y/Z/N strings")
+        return lib.PackedEops(packed)
+
+    def calculate(self, e_ops=None):
+        """Time-evolve |0...0> through the pulse schedule (qse/calc/qutip.py:34-53)."""
+        if self.amplitude is None or self.detuning is None:
+            raise Exception("The amplitude and detuning must be set before calculate().")
+        _check_pulses(self.amplitude, self.detuning)
+        t0 = time.time()
+        eng = self._engine_ready()
+        eng.set_option("tol", self.tol)
+        eng.set_option("fixed_terms", 4 if self.method == "rk4" else 0)
+        omega, delta, dt = flatten_schedule(self.amplitude, self.detuning)
+        eng.reset_state()
+        before = eng.metrics()
+        t1 = time.time()
+        exps = eng.evolve_schedule(omega, delta, dt, self._pack_eops(e_ops) if e_ops is not None else None)
+        t2 = time.time()
+        after = eng.metrics()
+        self._statevector = None
+        result = {}
+        if self.return_state:
+            result["state"] = self.statevector.reshape(-1, 1)
+        if e_ops is not None:
+            result["expectations"] = exps if exps is not None else np.zeros((omega.size, 0))
+        self.results = result
+        self.sij = None
+        self.spins = self.get_spins() if self.compute_spins else None
+        self.metrics = {
+            "steps": int(omega.size),
+            "hpsi_calls": int(after["hpsi_calls"] - before["hpsi_calls"]),
+            "kernel_launches": int(after["kernel_launches"] - before["kernel_launches"]),
+            "substeps": int(after["substeps"] - before["substeps"]),
+            "hpsi_passes": int(after["hpsi_passes"]),
+            "evolve_s": t2 - t1,
+            "total_s": time.time() - t0,
+        }
+        if self.wtimes:
+            print(f"time in compute and simulation = {self.metrics['evolve_s']} s.")
+            print(f"total time = {self.metrics['total_s']} s.")
+        return result
+
+    @property
+    def statevector(self):
+        """Flat (2^N,) complex128 final state (gathered over ranks when sharded), fetched lazily."""
+        if self._statevector is None:
+            if self._engine is None:
+                return None
+            local = self._engine.get_state()
+            if self._engine.nranks > 1:
+                from . import distributed as qdist
+
+                local = qdist.gather_shards(local)
+            self._statevector = local
+        return self._statevector
+
+    @statevector.setter
+    def statevector(self, value):
+        self._statevector = value
+
+    # ---- observables (override qse/calc/calculator.py:125-187) ------------------------------
+    def get_spins(self):
+        """(N, 3) <X_i>, <Y_i>, <Z_i> — qse.magnetic.get_spins on the device."""
+        if self.results is None:
+            self.calculate()
+        return self._engine.spins()
+
+    def get_sij(self):
+        """(N, N) spin correlation — qse.magnetic.get_sisj on the device; caches ``self.sij``."""
+        if self.results is None:
+            self.calculate()
+        self.sij = self._engine.sisj()
+        return self.sij
+
+    def get_number_operator(self):
+        """(N,) <n_i> — qse.magnetic.get_number_operator on the device."""
+        if self.results is None:
+            self.calculate()
+        return self._engine.number()
+
+    def structure_factor_from_sij(self, L1: int, L2: int, L3: int):
+        """Structure factor S[q] on the L1 x L2 x L3 reciprocal grid (host numpy, N <= 40).
+
+        The reference function raises TypeError (qse/magnetic.py:284: tuple @ Cell); this is the
+        DFT its docstring (qse/magnetic.py:251-256) defines — PARITY UNPINNED.
+        """
+        if self.sij is None:
+            self.get_sij()
+        from .magnetic import structure_factor_from_sij
+
+        return structure_factor_from_sij(L1, L2, L3, self.qbits, self.sij)
+
+    def bitstring_probabilities(self, k: int = 16):
+        """Top-k basis states as ``[(bitstring, probability), ...]`` (adiabatic.ipynb cell 8)."""
+        if self.results is None:
+            self.calculate()
+        n = self._nqbits()
+        idx, p = self._engine.topk(k)
+        return [(np.binary_repr(int(i), n), float(q)) for i, q in zip(idx, p) if int(i) < (1 << n)]

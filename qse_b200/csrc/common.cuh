@@ -1,0 +1,92 @@
+// common.cuh — device helpers shared by the libqsb kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef unsigned long long u64;
+
+#define QSB_DEV __device__ __forceinline__
+
+// ---- complex128 arithmetic on double2 --------------------------------------------------
+QSB_DEV double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+QSB_DEV void cacc(double2& a, double2 b) { a.x += b.x; a.y += b.y; }
+QSB_DEV double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+QSB_DEV double2 cscale(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
+QSB_DEV double cnorm2(double2 a) { return a.x * a.x + a.y * a.y; }
+// conj(a) * b
+QSB_DEV double2 cconj_mul(double2 a, double2 b) {
+    return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+
+// ---- warp-shuffle tree reductions (north_star: "Reductions use warp-shuffle trees") -----
+QSB_DEV double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+QSB_DEV double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// Sum over the CTA; result valid in thread 0.  scratch: >= 32 doubles of shared memory.
+QSB_DEV double block_sum(double v, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // scratch may still be read from a previous call
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    const int nwarp = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nwarp) ? scratch[threadIdx.x] : 0.0;
+    if (warp == 0) v = warp_sum(v);
+    return v;
+}
+QSB_DEV double block_max(double v, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    const int nwarp = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nwarp) ? scratch[threadIdx.x] : -1.0e308;
+    if (warp == 0) v = warp_max(v);
+    return v;
+}
+
+// ---- mbarrier + bulk async copy (TMA engine, 1-D: SASS UBLKCP) ---------------------------
+QSB_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+QSB_DEV void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+QSB_DEV void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+QSB_DEV void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+QSB_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "QSB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra QSB_DONE_%=;\n"
+        "bra QSB_WAIT_%=;\n"
+        "QSB_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; bytes multiple of 16, both addresses 16-byte aligned.
+QSB_DEV void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}

@@ -1,0 +1,218 @@
+// observe.cuh — diagonal builder (K1), Pauli-string reductions (K6), probabilities / top-k (K7).
+#pragma once
+#include "common.cuh"
+
+namespace qsb {
+
+// ---- K1: E_int[k] = sum_{i<j} V_ij b_i(k) b_j(k) ---------------------------------------------
+// Replaces ham_int = compute_interaction_hamiltonian(...).to_qutip() (qse/calc/qutip.py:61-64).
+// The pair terms are added in (i, j) lexicographic order starting from 0.0, the order
+// Operators.to_qutip (qse/operator/operators.py:41-44) adds them, without FMA contraction, so
+// the result is bit-identical to the sequential host sum (oracle: diagonal_energies).
+// vtab[i * n + j] (i < j) holds V_ij (0 when dropped by the 1e-8 cut-off).
+__global__ void __launch_bounds__(256) diag_build_kernel(double* __restrict__ eint, const double* __restrict__ vtab,
+                                                         int n, int nl, u64 rank_bits) {
+    extern __shared__ double vs[];
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) vs[i] = vtab[i];
+    __syncthreads();
+    const u64 dim = 1ull << nl;
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < dim; k += (u64)gridDim.x * blockDim.x) {
+        const u64 full = rank_bits | k;  // global basis index; qubit q <-> bit n-1-q
+        double e = 0.0;
+        u64 rest_i = full;
+        // iterate set bits from the most significant (qubit 0) downwards = i ascending
+        while (rest_i) {
+            const int bi = 63 - __clzll(rest_i);
+            rest_i &= ~(1ull << bi);
+            const int i = n - 1 - bi;
+            u64 rest_j = rest_i;  // bits below bi = qubits j > i
+            while (rest_j) {
+                const int bj = 63 - __clzll(rest_j);
+                rest_j &= ~(1ull << bj);
+                const double v = vs[i * n + (n - 1 - bj)];
+                if (v != 0.0) e = __dadd_rn(e, v);
+            }
+        }
+        eint[k] = e;
+    }
+}
+
+// min / max of a real vector: per-block partials {min, max}
+__global__ void __launch_bounds__(256) minmax_kernel(const double* __restrict__ v, u64 n, double* part) {
+    __shared__ double red[32];
+    double lo = 1.0e308, hi = -1.0e308;
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (u64)gridDim.x * blockDim.x) {
+        const double x = v[k];
+        lo = fmin(lo, x);
+        hi = fmax(hi, x);
+    }
+    const double bhi = block_max(hi, red);
+    const double blo = -block_max(-lo, red);
+    if (threadIdx.x == 0) {
+        part[2 * blockIdx.x] = blo;
+        part[2 * blockIdx.x + 1] = bhi;
+    }
+}
+__global__ void minmax_final_kernel(const double* part, int n, double* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double lo = 1.0e308, hi = -1.0e308;
+        for (int i = 0; i < n; ++i) {
+            lo = fmin(lo, part[2 * i]);
+            hi = fmax(hi, part[2 * i + 1]);
+        }
+        out[0] = lo;
+        out[1] = hi;
+    }
+}
+
+__global__ void __launch_bounds__(256) basis_state_kernel(double2* psi, u64 dim, u64 one_at) {
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < dim; k += (u64)gridDim.x * blockDim.x)
+        psi[k] = make_double2(k == one_at ? 1.0 : 0.0, 0.0);
+}
+
+__global__ void __launch_bounds__(256) copy_kernel(double2* __restrict__ dst, const double2* __restrict__ src, u64 dim) {
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < dim; k += (u64)gridDim.x * blockDim.x)
+        dst[k] = src[k];
+}
+
+// write-only sweep used to evict L2 between timed launches
+__global__ void __launch_bounds__(256) flush_kernel(double* buf, u64 n, double v) {
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (u64)gridDim.x * blockDim.x) buf[k] = v;
+}
+
+// ---- K6: generic Pauli-string reduction ---------------------------------------------------------
+//   r = sum_{k local, (k & nmask) == nmask} conj(a[k ^ flip]) * sgn(k) * b[k]
+// with sgn(k) = (-1)^popc(k & zmask)   (mode 0)     or     1 - (-1)^popc(k & zmask)   (mode 1).
+// <psi|P|psi> for P = X(xm) Y(ym) Z(zm) N(nm): flip = xm|ym, zmask = ym|zm, nmask = nm, times the
+// host-side factor i^popc(ym) (and the rank-dependent sign / selection of sharded bits).
+// `a` may point into a peer GPU's shard when the flip touches a sharded qubit.
+struct PauliArgs {
+    const double2* a;  // bra side: read at k ^ flip
+    const double2* b;  // ket side: read at k
+    u64 flip, zmask, nmask;
+    int mode;
+    int nl;
+    double* part;  // 2 doubles per block
+};
+__global__ void __launch_bounds__(256) pauli_kernel(const PauliArgs p) {
+    __shared__ double red[32];
+    const u64 dim = 1ull << p.nl;
+    double sr = 0.0, si = 0.0;
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < dim; k += (u64)gridDim.x * blockDim.x) {
+        if ((k & p.nmask) != p.nmask) continue;
+        const double sg = (__popcll(k & p.zmask) & 1) ? -1.0 : 1.0;
+        const double w = p.mode ? (1.0 - sg) : sg;
+        if (w == 0.0) continue;
+        const double2 bk = p.b[k];
+        const double2 ak = (p.flip == 0 && p.a == p.b) ? bk : p.a[k ^ p.flip];
+        const double2 c = cconj_mul(ak, bk);
+        sr += w * c.x;
+        si += w * c.y;
+    }
+    const double tr = block_sum(sr, red);
+    const double ti = block_sum(si, red);
+    if (threadIdx.x == 0) {
+        p.part[2 * blockIdx.x] = tr;
+        p.part[2 * blockIdx.x + 1] = ti;
+    }
+}
+// reduce the per-block {re, im} pairs into out[0..1]
+__global__ void __launch_bounds__(256) finalize_pair_kernel(const double* part, int n, double* out) {
+    __shared__ double red[32];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        a += part[2 * i];
+        b += part[2 * i + 1];
+    }
+    a = block_sum(a, red);
+    b = block_sum(b, red);
+    if (threadIdx.x == 0) {
+        out[0] = a;
+        out[1] = b;
+    }
+}
+
+// ---- <Z_q>, <n_q> for ALL local qubits and <psi|psi> in one pass ---------------------------------
+// out partials per block: [0] = sum p_k, [1 + q] = sum p_k * bit_q(k)  (q = local bit position)
+__global__ void __launch_bounds__(256) marginals_kernel(const double2* __restrict__ psi, int nl, double* part) {
+    __shared__ double red[32];
+    const u64 dim = 1ull << nl;
+    double tot = 0.0;
+    double cnt[QSB_MAX_QUBITS_DEV];
+#pragma unroll
+    for (int q = 0; q < QSB_MAX_QUBITS_DEV; ++q) cnt[q] = 0.0;
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < dim; k += (u64)gridDim.x * blockDim.x) {
+        const double pk = cnorm2(psi[k]);
+        tot += pk;
+#pragma unroll
+        for (int q = 0; q < QSB_MAX_QUBITS_DEV; ++q)
+            if ((k >> q) & 1ull) cnt[q] += pk;
+    }
+    const int stride = nl + 1;
+    const double t = block_sum(tot, red);
+    if (threadIdx.x == 0) part[(size_t)blockIdx.x * stride] = t;
+    for (int q = 0; q < nl; ++q) {
+        const double c = block_sum(cnt[q], red);
+        if (threadIdx.x == 0) part[(size_t)blockIdx.x * stride + 1 + q] = c;
+    }
+}
+__global__ void __launch_bounds__(256) finalize_rows_kernel(const double* part, int n_blocks, int stride, double* out) {
+    // one block per column
+    __shared__ double red[32];
+    const int col = blockIdx.x;
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) v += part[(size_t)i * stride + col];
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) out[col] = v;
+}
+
+// <a|b> = sum conj(a_k) b_k
+__global__ void __launch_bounds__(256) dot_kernel(const double2* __restrict__ a, const double2* __restrict__ b, u64 dim,
+                                                  double* part) {
+    __shared__ double red[32];
+    double sr = 0.0, si = 0.0;
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < dim; k += (u64)gridDim.x * blockDim.x) {
+        const double2 c = cconj_mul(a[k], b[k]);
+        sr += c.x;
+        si += c.y;
+    }
+    const double tr = block_sum(sr, red);
+    const double ti = block_sum(si, red);
+    if (threadIdx.x == 0) {
+        part[2 * blockIdx.x] = tr;
+        part[2 * blockIdx.x + 1] = ti;
+    }
+}
+
+__global__ void __launch_bounds__(256) prob_kernel(const double2* __restrict__ psi, double* __restrict__ out, u64 dim) {
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < dim; k += (u64)gridDim.x * blockDim.x)
+        out[k] = cnorm2(psi[k]);
+}
+
+// ---- K7: top-k by radix select on the composite key (probability desc, index asc) ---------------
+// A probability is a non-negative double: its bit pattern orders like the value.  One pass
+// histograms 16 bits of the key among the entries matching the prefix found so far.
+__global__ void __launch_bounds__(256) radix_hist_kernel(const double2* __restrict__ psi, u64 dim, u64 prefix,
+                                                         u64 prefix_mask, int shift, unsigned int* hist) {
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < dim; k += (u64)gridDim.x * blockDim.x) {
+        const u64 key = (u64)__double_as_longlong(cnorm2(psi[k]));
+        if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffffull], 1u);
+    }
+}
+// gather every entry with key > threshold, and those equal to it, into out (unordered)
+__global__ void __launch_bounds__(256) gather_ge_kernel(const double2* __restrict__ psi, u64 dim, u64 threshold,
+                                                        u64 index_base, u64* out_idx, double* out_p,
+                                                        unsigned int* counter, unsigned int cap) {
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < dim; k += (u64)gridDim.x * blockDim.x) {
+        const double pk = cnorm2(psi[k]);
+        if ((u64)__double_as_longlong(pk) >= threshold) {
+            const unsigned int slot = atomicAdd(counter, 1u);
+            if (slot < cap) {
+                out_idx[slot] = index_base + k;
+                out_p[slot] = pk;
+            }
+        }
+    }
+}
+
+}  // namespace qsb

@@ -1,0 +1,1050 @@
+// qsb.cu — libqsb: context, kernel launchers, Taylor stepper, observables and the C ABI of
+// include/qsb.h.  One context = one GPU (one shard of the state vector).
+#define QSB_MAX_QUBITS_DEV 34
+#include "../../include/qsb.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "hpsi.cuh"
+#include "nccl_dl.h"
+#include "observe.cuh"
+
+using namespace qsb;
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+struct qsb_ctx {
+    int n = 0, p = 0, nl = 0, rank = 0, nranks = 1, device = 0;
+    u64 dim = 0;        // amplitudes in this shard
+    u64 rank_bits = 0;  // rank << nl
+    int pop_rank = 0;
+    int n_sm = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double2 *psi = nullptr, *wa = nullptr, *wb = nullptr;
+    double* eint = nullptr;
+    double* vtab = nullptr;
+    bool have_v = false;
+    double diag_min = 0.0, diag_max = 0.0;
+    double* part = nullptr;  // per-block partials
+    size_t part_n = 0;
+    double* slots = nullptr;  // device result slots
+    double* h_slots = nullptr;
+    size_t slots_n = 0;
+    HpsiPlan plan;
+    // options
+    double tol = 1e-14, theta_max = 3.0;
+    int max_terms = 64, fixed_terms = 0, force_flat = 0;
+    int m_prev = 0;
+    // sharding
+    nccl_comm_t comm = nullptr;
+    bool ipc = false;
+    double2* peer_psi[64] = {nullptr};
+    double2* peer_wa[64] = {nullptr};
+    double2* peer_wb[64] = {nullptr};
+    double2* stage[kMaxPeers] = {nullptr};  // NCCL-staged partner shards when IPC is unavailable
+    // measurement
+    double* flush_buf = nullptr;
+    size_t flush_n = 0;
+    qsb_metrics met;
+    char err[512] = "";
+};
+
+static int fail(qsb_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    snprintf(g_err, sizeof(g_err), "%s", buf);
+    if (c) snprintf(c->err, sizeof(c->err), "%s", buf);
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(c, QSB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                       \
+    } while (0)
+#define NC(call)                                                                                      \
+    do {                                                                                              \
+        int r_ = (call);                                                                              \
+        if (r_ != kNcclSuccess)                                                                       \
+            return fail(c, QSB_ERR_NCCL, "%s failed: %s (%s:%d)", #call, nccl_api()->GetErrorString(r_), \
+                        __FILE__, __LINE__);                                                          \
+    } while (0)
+#define TRY(call)              \
+    do {                       \
+        int r_ = (call);       \
+        if (r_ != QSB_OK) return r_; \
+    } while (0)
+#define LAUNCHED(c) ((c)->met.kernel_launches++)
+
+static int check_launch(qsb_ctx* c, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(c, QSB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return QSB_OK;
+}
+
+static int grid_for(const qsb_ctx* c, u64 work, int per_block) {
+    const u64 need = (work + per_block - 1) / per_block;
+    const u64 cap = (u64)c->n_sm * 8;
+    return (int)std::max<u64>(1, std::min<u64>(need, cap));
+}
+
+// ------------------------------------------------------------------------------------------------
+// collectives on small device arrays
+// ------------------------------------------------------------------------------------------------
+static int allreduce(qsb_ctx* c, double* dev, size_t count, int op) {
+    if (c->nranks == 1) return QSB_OK;
+    NC(nccl_api()->AllReduce(dev, dev, count, kNcclFloat64, op, c->comm, c->stream));
+    return QSB_OK;
+}
+// stream-ordered barrier across ranks (a 1-double all-reduce on a scratch slot)
+static int rank_barrier(qsb_ctx* c) {
+    if (c->nranks == 1) return QSB_OK;
+    return allreduce(c, c->slots + c->slots_n - 1, 1, kNcclSum);
+}
+static int fetch_slots(qsb_ctx* c, size_t first, size_t count) {
+    CU(cudaMemcpyAsync(c->h_slots + first, c->slots + first, count * sizeof(double), cudaMemcpyDeviceToHost,
+                       c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return QSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// H psi launcher
+// ------------------------------------------------------------------------------------------------
+static const double2* peer_of(qsb_ctx* c, const double2* x, int partner) {
+    if (x == c->psi) return c->peer_psi[partner];
+    if (x == c->wa) return c->peer_wa[partner];
+    if (x == c->wb) return c->peer_wb[partner];
+    return nullptr;
+}
+
+// y <- scale * H(omega, delta) x   [fuse: acc += y (acc may be null), *norm_slot <- |y|^2 of this shard]
+static int launch_hpsi(qsb_ctx* c, const double2* x, double2* y, double omega, double delta, bool fuse,
+                       double2 scale, double2* acc, double* norm_slot) {
+    if (!c->have_v) return fail(c, QSB_ERR_STATE, "qsb_set_interaction has not been called");
+    const double2* peers[kMaxPeers] = {nullptr, nullptr, nullptr};
+    if (c->p > kMaxPeers) return fail(c, QSB_ERR_UNSUPPORTED, "more than %d sharded qubits", kMaxPeers);
+    for (int g = 0; g < c->p; ++g) {
+        const int partner = c->rank ^ (1 << g);
+        if (c->ipc) {
+            peers[g] = peer_of(c, x, partner);
+            if (!peers[g]) return fail(c, QSB_ERR_STATE, "H psi input is not an exported buffer");
+        } else {
+            NC(nccl_api()->GroupStart());
+            NC(nccl_api()->Send(x, c->dim * 2, kNcclFloat64, partner, c->comm, c->stream));
+            NC(nccl_api()->Recv(c->stage[g], c->dim * 2, kNcclFloat64, partner, c->comm, c->stream));
+            NC(nccl_api()->GroupEnd());
+            peers[g] = c->stage[g];
+        }
+    }
+    c->met.hpsi_calls++;
+    if (!c->plan.tiled) {
+        HpsiFlat a{};
+        a.x = x;
+        a.y = y;
+        a.eint = c->eint;
+        a.acc = fuse ? acc : nullptr;
+        a.norm_part = (fuse && norm_slot) ? c->part : nullptr;
+        for (int g = 0; g < kMaxPeers; ++g) a.peer[g] = peers[g];
+        a.n_peer = c->p;
+        a.half_omega = 0.5 * omega;
+        a.delta = delta;
+        a.scale = scale;
+        a.nl = c->nl;
+        a.pop_rank = c->pop_rank;
+        a.fuse = fuse ? 1 : 0;
+        const int grid = grid_for(c, c->dim, 256);
+        hpsi_flat_kernel<<<grid, 256, 0, c->stream>>>(a);
+        LAUNCHED(c);
+        TRY(check_launch(c, "hpsi_flat_kernel"));
+        if (fuse && norm_slot) {
+            finalize_sum_kernel<<<1, 256, 0, c->stream>>>(c->part, grid, norm_slot);
+            LAUNCHED(c);
+        }
+        return check_launch(c, "finalize_sum_kernel");
+    }
+    const u64 n_tiles = c->dim >> kTileBits;
+    const int grid = (int)std::min<u64>(n_tiles, (u64)c->n_sm);
+    for (int i = 0; i < c->plan.n_pass; ++i) {
+        const bool first = (i == 0), last = (i == c->plan.n_pass - 1);
+        HpsiPass a{};
+        a.x = x;
+        a.y = y;
+        a.eint = c->eint;
+        a.acc = (fuse && last) ? acc : nullptr;
+        a.norm_part = (fuse && last && norm_slot) ? c->part : nullptr;
+        for (int g = 0; g < kMaxPeers; ++g) a.peer[g] = peers[g];
+        a.n_peer = first ? c->p : 0;
+        a.half_omega = 0.5 * omega;
+        a.delta = delta;
+        a.scale = fuse ? scale : make_double2(1.0, 0.0);
+        a.nl = c->nl;
+        a.lb = c->plan.pass[i].lb;
+        a.hb = c->plan.pass[i].hb;
+        a.hb0 = c->plan.pass[i].hb0;
+        a.pop_rank = c->pop_rank;
+        a.n_tiles = n_tiles;
+        // LAST without fuse is a plain pass: scale = 1, no acc, no norm
+        if (first && last) hpsi_tile_kernel<true, true><<<grid, kThreads, kTileSmemBytes, c->stream>>>(a);
+        else if (first) hpsi_tile_kernel<true, false><<<grid, kThreads, kTileSmemBytes, c->stream>>>(a);
+        else if (last) hpsi_tile_kernel<false, true><<<grid, kThreads, kTileSmemBytes, c->stream>>>(a);
+        else hpsi_tile_kernel<false, false><<<grid, kThreads, kTileSmemBytes, c->stream>>>(a);
+        LAUNCHED(c);
+        TRY(check_launch(c, "hpsi_tile_kernel"));
+    }
+    if (fuse && norm_slot) {
+        finalize_sum_kernel<<<1, 256, 0, c->stream>>>(c->part, grid, norm_slot);
+        LAUNCHED(c);
+        TRY(check_launch(c, "finalize_sum_kernel"));
+    }
+    return QSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Taylor stepper (fused K4): psi <- sum_j (-i H dt)^j / j! psi, norm-terminated, sub-stepped
+// ------------------------------------------------------------------------------------------------
+static double spectral_bound(const qsb_ctx* c, double omega, double delta) {
+    const double hi = c->diag_max + std::max(-delta, 0.0) * c->n;
+    const double lo = c->diag_min - std::max(delta, 0.0) * c->n;
+    return std::max(fabs(hi), fabs(lo)) + 0.5 * fabs(omega) * c->n;
+}
+
+static int copy_vec(qsb_ctx* c, double2* dst, const double2* src) {
+    copy_kernel<<<grid_for(c, c->dim, 256), 256, 0, c->stream>>>(dst, src, c->dim);
+    LAUNCHED(c);
+    return check_launch(c, "copy_kernel");
+}
+
+static int evolve_segment_impl(qsb_ctx* c, double omega, double delta, double dt, int* n_hpsi) {
+    const double theta = spectral_bound(c, omega, delta) * fabs(dt);
+    const int nsub = std::max(1, (int)ceil(theta / c->theta_max));
+    const double h = dt / nsub;
+    const double theta_sub = theta / nsub;
+    c->met.segments++;
+    c->met.last_theta = theta;
+    int applied = 0;
+    if (dt == 0.0) {
+        if (n_hpsi) *n_hpsi = 0;
+        return QSB_OK;
+    }
+    // x may alias the accumulator psi only when every amplitude of x is read by the CTA that
+    // updates it, after the read: true for the tiled single-GPU path, false for the untiled
+    // kernel and whenever peers read x over NVLink while psi is being updated.
+    const bool need_copy = !c->plan.tiled || c->nranks > 1;
+    for (int sub = 0; sub < nsub; ++sub) {
+        c->met.substeps++;
+        const double2* x = c->psi;
+        if (need_copy) {
+            TRY(copy_vec(c, c->wb, c->psi));
+            TRY(rank_barrier(c));  // partners must see the finished copy before they read it
+            x = c->wb;
+        }
+        bool converged = false;
+        int j = 1;
+        for (; j <= c->max_terms; ++j) {
+            double2* y = (j & 1) ? c->wa : c->wb;
+            const double2 scale = make_double2(0.0, -h / (double)j);  // -i h / j
+            double* slot = c->slots + j;
+            TRY(launch_hpsi(c, x, y, omega, delta, true, scale, c->psi, slot));
+            ++applied;
+            // the all-reduce doubles as the cross-rank barrier that orders peer reads of y
+            TRY(allreduce(c, slot, 1, kNcclSum));
+            x = y;
+            if (c->fixed_terms > 0) {
+                if (j == c->fixed_terms) {
+                    converged = true;
+                    break;
+                }
+                continue;
+            }
+            if (j >= c->m_prev - 1) {
+                TRY(fetch_slots(c, j, 1));
+                const double nrm = sqrt(c->h_slots[j]);
+                if (!(nrm == nrm)) return fail(c, QSB_ERR_NOCONV, "Taylor term %d is NaN (|H|dt bound %.3g)", j, theta_sub);
+                if (nrm <= c->tol && (double)j >= theta_sub) {
+                    converged = true;
+                    break;
+                }
+            }
+        }
+        if (!converged)
+            return fail(c, QSB_ERR_NOCONV, "Taylor series did not reach tol=%.1e in %d terms (|H|dt bound %.3g)",
+                        c->tol, c->max_terms, theta_sub);
+        c->m_prev = j;
+        c->met.last_terms = j;
+    }
+    if (n_hpsi) *n_hpsi = applied;
+    return QSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// observables
+// ------------------------------------------------------------------------------------------------
+struct TermResult {
+    double re, im;
+};
+
+// evaluate <psi|term_t|psi> (coef excluded) for a batch of Pauli terms into host results
+static int pauli_batch(qsb_ctx* c, int64_t n_terms, const u64* xm, const u64* ym, const u64* zm, const u64* nm,
+                       TermResult* out) {
+    const u64 lmask = c->dim - 1ull;
+    const size_t cap = (c->slots_n - 2) / 2;
+    const int grid = grid_for(c, c->dim, 256);
+    std::vector<double> sign;
+    for (int64_t t0 = 0; t0 < n_terms; t0 += (int64_t)cap) {
+        const int64_t nb = std::min<int64_t>((int64_t)cap, n_terms - t0);
+        sign.assign((size_t)nb, 0.0);  // 0: this shard contributes nothing to the term
+        CU(cudaMemsetAsync(c->slots, 0, (size_t)nb * 2 * sizeof(double), c->stream));
+        for (int64_t t = 0; t < nb; ++t) {
+            const u64 x = xm[t0 + t], y = ym[t0 + t], z = zm[t0 + t], nmk = nm[t0 + t];
+            if ((x & y) | (x & z) | (x & nmk) | (y & z) | (y & nmk) | (z & nmk))
+                return fail(c, QSB_ERR_INVALID, "Pauli term %lld: masks overlap", (long long)(t0 + t));
+            if ((x | y | z | nmk) >> c->n)
+                return fail(c, QSB_ERR_INVALID, "Pauli term %lld: mask beyond qubit count", (long long)(t0 + t));
+            const u64 flip = x | y, zz = y | z;
+            const u64 rank = (u64)c->rank;
+            const u64 flip_g = flip >> c->nl, zz_g = zz >> c->nl, n_g = nmk >> c->nl;
+            if ((rank & n_g) != n_g) continue;  // this shard has a 0 where N projects on 1
+            PauliArgs a{};
+            a.b = c->psi;
+            a.a = c->psi;
+            if (flip_g) {
+                if (!c->ipc)
+                    return fail(c, QSB_ERR_UNSUPPORTED,
+                                "Pauli term flips a sharded qubit and peer memory is not mapped");
+                a.a = c->peer_psi[rank ^ flip_g];
+            }
+            a.flip = flip & lmask;
+            a.zmask = zz & lmask;
+            a.nmask = nmk & lmask;
+            a.mode = 0;
+            a.nl = c->nl;
+            a.part = c->part;
+            sign[(size_t)t] = (__builtin_popcountll(rank & zz_g) & 1) ? -1.0 : 1.0;  // sharded Z / Y bits
+            pauli_kernel<<<grid, 256, 0, c->stream>>>(a);
+            LAUNCHED(c);
+            TRY(check_launch(c, "pauli_kernel"));
+            finalize_pair_kernel<<<1, 256, 0, c->stream>>>(c->part, grid, c->slots + 2 * t);
+            LAUNCHED(c);
+            TRY(check_launch(c, "finalize_pair_kernel"));
+        }
+        TRY(fetch_slots(c, 0, (size_t)nb * 2));
+        for (int64_t t = 0; t < nb; ++t) {
+            c->h_slots[2 * t] *= sign[(size_t)t];
+            c->h_slots[2 * t + 1] *= sign[(size_t)t];
+        }
+        if (c->nranks > 1) {
+            CU(cudaMemcpyAsync(c->slots, c->h_slots, (size_t)nb * 2 * sizeof(double), cudaMemcpyHostToDevice,
+                               c->stream));
+            TRY(allreduce(c, c->slots, (size_t)nb * 2, kNcclSum));
+            TRY(fetch_slots(c, 0, (size_t)nb * 2));
+        }
+        for (int64_t t = 0; t < nb; ++t) {
+            const int ny = __builtin_popcountll(ym[t0 + t]) & 3;  // global factor i^ny of the Y's
+            const double re = c->h_slots[2 * t], im = c->h_slots[2 * t + 1];
+            TermResult r;
+            switch (ny) {
+                case 0: r = {re, im}; break;
+                case 1: r = {-im, re}; break;
+                case 2: r = {-re, -im}; break;
+                default: r = {im, -re}; break;
+            }
+            out[t0 + t] = r;
+        }
+    }
+    return QSB_OK;
+}
+
+// probabilities' marginals: tot = <psi|psi>, cnt[q] = <n_q> for global qubit q (whole register)
+static int marginals(qsb_ctx* c, double* tot, double* number /* n */) {
+    const int grid = std::min(grid_for(c, c->dim, 256), c->n_sm * 2);
+    const int stride = c->nl + 1;
+    if ((size_t)grid * stride > c->part_n) return fail(c, QSB_ERR_STATE, "partials buffer too small");
+    marginals_kernel<<<grid, 256, 0, c->stream>>>(c->psi, c->nl, c->part);
+    LAUNCHED(c);
+    TRY(check_launch(c, "marginals_kernel"));
+    finalize_rows_kernel<<<stride, 256, 0, c->stream>>>(c->part, grid, stride, c->slots);
+    LAUNCHED(c);
+    TRY(check_launch(c, "finalize_rows_kernel"));
+    TRY(fetch_slots(c, 0, (size_t)stride));
+    // lay out per global qubit: qubit q <-> bit n-1-q; bits >= nl are rank bits
+    std::vector<double> v(c->n + 1, 0.0);
+    v[0] = c->h_slots[0];
+    for (int q = 0; q < c->n; ++q) {
+        const int bit = c->n - 1 - q;
+        if (bit < c->nl) v[1 + q] = c->h_slots[1 + bit];
+        else v[1 + q] = ((c->rank >> (bit - c->nl)) & 1) ? c->h_slots[0] : 0.0;
+    }
+    if (c->nranks > 1) {
+        CU(cudaMemcpyAsync(c->slots, v.data(), (size_t)(c->n + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        TRY(allreduce(c, c->slots, (size_t)(c->n + 1), kNcclSum));
+        TRY(fetch_slots(c, 0, (size_t)(c->n + 1)));
+        for (int i = 0; i <= c->n; ++i) v[i] = c->h_slots[i];
+    }
+    if (tot) *tot = v[0];
+    if (number)
+        for (int q = 0; q < c->n; ++q) number[q] = v[1 + q];
+    return QSB_OK;
+}
+
+static int energy_impl(qsb_ctx* c, double omega, double delta, double* out) {
+    TRY(rank_barrier(c));
+    TRY(launch_hpsi(c, c->psi, c->wa, omega, delta, false, make_double2(1.0, 0.0), nullptr, nullptr));
+    const int grid = grid_for(c, c->dim, 256);
+    dot_kernel<<<grid, 256, 0, c->stream>>>(c->psi, c->wa, c->dim, c->part);
+    LAUNCHED(c);
+    TRY(check_launch(c, "dot_kernel"));
+    finalize_pair_kernel<<<1, 256, 0, c->stream>>>(c->part, grid, c->slots);
+    LAUNCHED(c);
+    TRY(check_launch(c, "finalize_pair_kernel"));
+    TRY(allreduce(c, c->slots, 2, kNcclSum));
+    TRY(fetch_slots(c, 0, 2));
+    *out = c->h_slots[0];
+    return QSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sharding set-up: NCCL communicator + CUDA-IPC mapping of every peer's psi / wa / wb
+// ------------------------------------------------------------------------------------------------
+static int setup_comm(qsb_ctx* c, const void* uid_bytes) {
+    NcclApi* api = nccl_api();
+    if (!api->ok) return fail(c, QSB_ERR_NCCL, "%s", api->why);
+    nccl_uid_t uid;
+    memcpy(&uid, uid_bytes, sizeof(uid));
+    NC(api->CommInitRank(&c->comm, c->nranks, uid, c->rank));
+
+    // exchange IPC handles of the three state-sized buffers
+    const size_t hsz = sizeof(cudaIpcMemHandle_t);
+    const size_t rec = 3 * hsz;
+    std::vector<unsigned char> mine(rec), all(rec * c->nranks);
+    bool ok = getenv("QSB_NO_IPC") == nullptr;
+    cudaIpcMemHandle_t h[3];
+    double2* bufs[3] = {c->psi, c->wa, c->wb};
+    for (int i = 0; i < 3 && ok; ++i) {
+        if (cudaIpcGetMemHandle(&h[i], bufs[i]) != cudaSuccess) {
+            ok = false;
+            cudaGetLastError();
+        } else {
+            memcpy(mine.data() + i * hsz, &h[i], hsz);
+        }
+    }
+    unsigned char *d_mine = nullptr, *d_all = nullptr;
+    CU(cudaMalloc(&d_mine, rec + 8));
+    CU(cudaMalloc(&d_all, (rec + 8) * c->nranks));
+    // record = handles + an "ok" flag so that every rank takes the same decision
+    std::vector<unsigned char> rec_mine(rec + 8, 0), rec_all((rec + 8) * c->nranks, 0);
+    memcpy(rec_mine.data(), mine.data(), rec);
+    rec_mine[rec] = ok ? 1 : 0;
+    CU(cudaMemcpyAsync(d_mine, rec_mine.data(), rec + 8, cudaMemcpyHostToDevice, c->stream));
+    NC(api->AllGather(d_mine, d_all, rec + 8, kNcclUint8, c->comm, c->stream));
+    CU(cudaMemcpyAsync(rec_all.data(), d_all, (rec + 8) * c->nranks, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_mine);
+    cudaFree(d_all);
+    for (int r = 0; r < c->nranks; ++r) ok = ok && rec_all[(rec + 8) * r + rec] == 1;
+    if (ok) {
+        for (int r = 0; r < c->nranks && ok; ++r) {
+            if (r == c->rank) {
+                c->peer_psi[r] = c->psi;
+                c->peer_wa[r] = c->wa;
+                c->peer_wb[r] = c->wb;
+                continue;
+            }
+            double2** dst[3] = {&c->peer_psi[r], &c->peer_wa[r], &c->peer_wb[r]};
+            for (int i = 0; i < 3; ++i) {
+                cudaIpcMemHandle_t hh;
+                memcpy(&hh, rec_all.data() + (rec + 8) * r + i * hsz, hsz);
+                void* ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, hh, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    ok = false;
+                    break;
+                }
+                *dst[i] = (double2*)ptr;
+            }
+        }
+    }
+    // agree on the outcome (an open can fail on one rank only)
+    c->h_slots[0] = ok ? 0.0 : 1.0;
+    CU(cudaMemcpyAsync(c->slots, c->h_slots, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    TRY(allreduce(c, c->slots, 1, kNcclSum));
+    TRY(fetch_slots(c, 0, 1));
+    c->ipc = (c->h_slots[0] == 0.0);
+    if (!c->ipc) {
+        for (int g = 0; g < c->p; ++g) CU(cudaMalloc(&c->stage[g], c->dim * sizeof(double2)));
+    }
+    return QSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int qsb_abi_version(void) { return QSB_ABI_VERSION; }
+
+const char* qsb_build_info(void) {
+    return "libqsb sm_100a; tile 2^12 amplitudes, 512 threads, 2-stage bulk-copy pipeline; built " __DATE__;
+}
+
+int qsb_device_count(int* count) {
+    qsb_ctx* c = nullptr;
+    if (!count) return fail(c, QSB_ERR_INVALID, "count is NULL");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(c, QSB_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return QSB_OK;
+}
+
+const char* qsb_last_error(const qsb_ctx* ctx) { return ctx ? ctx->err : g_err; }
+
+int qsb_nccl_unique_id(void* out_uid) {
+    qsb_ctx* c = nullptr;
+    if (!out_uid) return fail(c, QSB_ERR_INVALID, "out_uid is NULL");
+    NcclApi* api = nccl_api();
+    if (!api->ok) return fail(c, QSB_ERR_NCCL, "%s", api->why);
+    nccl_uid_t uid;
+    NC(api->GetUniqueId(&uid));
+    memcpy(out_uid, &uid, sizeof(uid));
+    return QSB_OK;
+}
+
+int qsb_create_sharded(int n_qubits, int device, int rank, int nranks, const void* nccl_uid, qsb_ctx** out) {
+    qsb_ctx* c = nullptr;
+    if (!out) return fail(c, QSB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_qubits < 1 || n_qubits > QSB_MAX_QUBITS) return fail(c, QSB_ERR_INVALID, "n_qubits=%d out of range", n_qubits);
+    if (nranks < 1 || (nranks & (nranks - 1)) || nranks > 64)
+        return fail(c, QSB_ERR_INVALID, "nranks=%d must be a power of two <= 64", nranks);
+    if (rank < 0 || rank >= nranks) return fail(c, QSB_ERR_INVALID, "rank=%d out of range", rank);
+    int p = 0;
+    while ((1 << p) < nranks) ++p;
+    if (p > n_qubits - 1 && nranks > 1) return fail(c, QSB_ERR_INVALID, "more ranks than half the basis");
+    if (n_qubits - p > QSB_MAX_QUBITS_DEV - 1) return fail(c, QSB_ERR_INVALID, "shard of 2^%d amplitudes is too large", n_qubits - p);
+    if (nranks > 1 && !nccl_uid) return fail(c, QSB_ERR_INVALID, "nccl_uid is NULL");
+
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(c, QSB_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    c = new qsb_ctx();
+    memset(&c->met, 0, sizeof(c->met));
+    c->n = n_qubits;
+    c->p = p;
+    c->nl = n_qubits - p;
+    c->rank = rank;
+    c->nranks = nranks;
+    c->device = device;
+    c->dim = 1ull << c->nl;
+    c->rank_bits = (u64)rank << c->nl;
+    c->pop_rank = __builtin_popcount((unsigned)rank);
+    int rc = QSB_OK;
+    do {
+        cudaDeviceProp prop;
+        if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { rc = fail(c, QSB_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); break; }
+        if (prop.major < 10) { rc = fail(c, QSB_ERR_UNSUPPORTED, "device %d is sm_%d%d; libqsb is built for sm_100a only", device, prop.major, prop.minor); break; }
+        c->n_sm = prop.multiProcessorCount;
+#define CUB(call) if ((e = (call)) != cudaSuccess) { rc = fail(c, QSB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e)); break; }
+        CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CUB(cudaEventCreate(&c->ev0));
+        CUB(cudaEventCreate(&c->ev1));
+        CUB(cudaMalloc(&c->psi, c->dim * sizeof(double2)));
+        CUB(cudaMalloc(&c->wa, c->dim * sizeof(double2)));
+        CUB(cudaMalloc(&c->wb, c->dim * sizeof(double2)));
+        CUB(cudaMalloc(&c->eint, c->dim * sizeof(double)));
+        CUB(cudaMalloc(&c->vtab, (size_t)n_qubits * n_qubits * sizeof(double)));
+        c->part_n = (size_t)c->n_sm * 8 * (QSB_MAX_QUBITS_DEV + 2);
+        CUB(cudaMalloc(&c->part, c->part_n * sizeof(double)));
+        c->slots_n = 8192;
+        CUB(cudaMalloc(&c->slots, c->slots_n * sizeof(double)));
+        CUB(cudaMemset(c->slots, 0, c->slots_n * sizeof(double)));
+        CUB(cudaMallocHost(&c->h_slots, c->slots_n * sizeof(double)));
+        CUB(cudaFuncSetAttribute(hpsi_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+        CUB(cudaFuncSetAttribute(hpsi_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+        CUB(cudaFuncSetAttribute(hpsi_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+        CUB(cudaFuncSetAttribute(hpsi_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+#undef CUB
+        c->plan = make_plan(c->nl, false);
+        if (nranks > 1) rc = setup_comm(c, nccl_uid);
+    } while (0);
+    if (rc != QSB_OK) {
+        snprintf(g_err, sizeof(g_err), "%s", c->err);
+        qsb_destroy(c);
+        return rc;
+    }
+    rc = qsb_reset_state(c);
+    if (rc != QSB_OK) {
+        qsb_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return QSB_OK;
+}
+
+int qsb_create(int n_qubits, int device, qsb_ctx** out) {
+    return qsb_create_sharded(n_qubits, device, 0, 1, nullptr, out);
+}
+
+int qsb_destroy(qsb_ctx* c) {
+    if (!c) return QSB_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->ipc) {
+        for (int r = 0; r < c->nranks; ++r) {
+            if (r == c->rank) continue;
+            if (c->peer_psi[r]) cudaIpcCloseMemHandle(c->peer_psi[r]);
+            if (c->peer_wa[r]) cudaIpcCloseMemHandle(c->peer_wa[r]);
+            if (c->peer_wb[r]) cudaIpcCloseMemHandle(c->peer_wb[r]);
+        }
+    }
+    if (c->comm && nccl_api()->ok) nccl_api()->CommDestroy(c->comm);
+    for (int g = 0; g < kMaxPeers; ++g) cudaFree(c->stage[g]);
+    cudaFree(c->psi);
+    cudaFree(c->wa);
+    cudaFree(c->wb);
+    cudaFree(c->eint);
+    cudaFree(c->vtab);
+    cudaFree(c->part);
+    cudaFree(c->slots);
+    cudaFree(c->flush_buf);
+    if (c->h_slots) cudaFreeHost(c->h_slots);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
+    return QSB_OK;
+}
+
+int qsb_local_dim(const qsb_ctx* ctx, uint64_t* dim) {
+    if (!ctx || !dim) return fail(nullptr, QSB_ERR_INVALID, "NULL argument");
+    *dim = ctx->dim;
+    return QSB_OK;
+}
+
+int qsb_set_option(qsb_ctx* c, const char* key, double value) {
+    if (!c || !key) return fail(c, QSB_ERR_INVALID, "NULL argument");
+    if (!strcmp(key, "tol")) {
+        if (!(value > 0.0)) return fail(c, QSB_ERR_INVALID, "tol must be positive");
+        c->tol = value;
+    } else if (!strcmp(key, "theta_max")) {
+        if (!(value > 0.0)) return fail(c, QSB_ERR_INVALID, "theta_max must be positive");
+        c->theta_max = value;
+    } else if (!strcmp(key, "max_terms")) {
+        if (value < 1 || value > 4000) return fail(c, QSB_ERR_INVALID, "max_terms out of range");
+        c->max_terms = (int)value;
+    } else if (!strcmp(key, "fixed_terms")) {
+        if (value < 0 || value > 4000) return fail(c, QSB_ERR_INVALID, "fixed_terms out of range");
+        c->fixed_terms = (int)value;
+    } else if (!strcmp(key, "hpsi_path")) {
+        c->force_flat = value != 0.0;
+        c->plan = make_plan(c->nl, c->force_flat);
+    } else {
+        return fail(c, QSB_ERR_INVALID, "unknown option '%s'", key);
+    }
+    if ((size_t)c->max_terms + 2 > c->slots_n) return fail(c, QSB_ERR_INVALID, "max_terms too large");
+    return QSB_OK;
+}
+
+int qsb_set_interaction(qsb_ctx* c, const double* v) {
+    if (!c || !v) return fail(c, QSB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    const int n = c->n;
+    std::vector<double> tab((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j) {
+            const double x = v[(size_t)i * n + j];
+            if (!(x == x) || isinf(x)) return fail(c, QSB_ERR_INVALID, "V[%d,%d] is not finite", i, j);
+            tab[(size_t)i * n + j] = x;
+        }
+    CU(cudaMemcpyAsync(c->vtab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const int grid = grid_for(c, c->dim, 256);
+    diag_build_kernel<<<grid, 256, (size_t)n * n * sizeof(double), c->stream>>>(c->eint, c->vtab, n, c->nl, c->rank_bits);
+    LAUNCHED(c);
+    TRY(check_launch(c, "diag_build_kernel"));
+    minmax_kernel<<<grid, 256, 0, c->stream>>>(c->eint, c->dim, c->part);
+    LAUNCHED(c);
+    TRY(check_launch(c, "minmax_kernel"));
+    minmax_final_kernel<<<1, 32, 0, c->stream>>>(c->part, grid, c->slots);
+    LAUNCHED(c);
+    TRY(check_launch(c, "minmax_final_kernel"));
+    TRY(fetch_slots(c, 0, 2));
+    double lo = c->h_slots[0], hi = c->h_slots[1];
+    if (c->nranks > 1) {
+        c->h_slots[0] = -lo;
+        c->h_slots[1] = hi;
+        CU(cudaMemcpyAsync(c->slots, c->h_slots, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        TRY(allreduce(c, c->slots, 2, kNcclMax));
+        TRY(fetch_slots(c, 0, 2));
+        lo = -c->h_slots[0];
+        hi = c->h_slots[1];
+    }
+    c->diag_min = lo;
+    c->diag_max = hi;
+    c->have_v = true;
+    c->m_prev = 0;
+    return QSB_OK;
+}
+
+int qsb_get_diagonal(qsb_ctx* c, double* out) {
+    if (!c || !out) return fail(c, QSB_ERR_INVALID, "NULL argument");
+    if (!c->have_v) return fail(c, QSB_ERR_STATE, "qsb_set_interaction has not been called");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(out, c->eint, c->dim * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return QSB_OK;
+}
+
+int qsb_reset_state(qsb_ctx* c) {
+    if (!c) return fail(c, QSB_ERR_INVALID, "NULL context");
+    CU(cudaSetDevice(c->device));
+    const u64 one_at = (c->rank == 0) ? 0ull : ~0ull;
+    basis_state_kernel<<<grid_for(c, c->dim, 256), 256, 0, c->stream>>>(c->psi, c->dim, one_at);
+    LAUNCHED(c);
+    TRY(check_launch(c, "basis_state_kernel"));
+    CU(cudaStreamSynchronize(c->stream));
+    return QSB_OK;
+}
+
+int qsb_set_state(qsb_ctx* c, const double* re_im) {
+    if (!c || !re_im) return fail(c, QSB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(c->psi, re_im, c->dim * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return QSB_OK;
+}
+
+int qsb_get_state(qsb_ctx* c, double* re_im) {
+    if (!c || !re_im) return fail(c, QSB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(re_im, c->psi, c->dim * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return QSB_OK;
+}
+
+int qsb_apply_h(qsb_ctx* c, double omega, double delta) {
+    if (!c) return fail(c, QSB_ERR_INVALID, "NULL context");
+    CU(cudaSetDevice(c->device));
+    TRY(rank_barrier(c));
+    TRY(launch_hpsi(c, c->psi, c->wa, omega, delta, false, make_double2(1.0, 0.0), nullptr, nullptr));
+    TRY(rank_barrier(c));
+    CU(cudaStreamSynchronize(c->stream));
+    return QSB_OK;
+}
+
+int qsb_get_work(qsb_ctx* c, double* re_im) {
+    if (!c || !re_im) return fail(c, QSB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(re_im, c->wa, c->dim * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return QSB_OK;
+}
+
+int qsb_evolve_segment(qsb_ctx* c, double omega, double delta, double dt_us, int* n_hpsi) {
+    if (!c) return fail(c, QSB_ERR_INVALID, "NULL context");
+    if (!c->have_v) return fail(c, QSB_ERR_STATE, "qsb_set_interaction has not been called");
+    CU(cudaSetDevice(c->device));
+    TRY(evolve_segment_impl(c, omega, delta, dt_us, n_hpsi));
+    CU(cudaStreamSynchronize(c->stream));
+    return QSB_OK;
+}
+
+int qsb_expect_pauli(qsb_ctx* c, int64_t n_terms, const double* coef, const uint64_t* xmask, const uint64_t* ymask,
+                     const uint64_t* zmask, const uint64_t* nmask, double* out_re_im) {
+    if (!c || (n_terms > 0 && (!coef || !xmask || !ymask || !zmask || !nmask || !out_re_im)))
+        return fail(c, QSB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    TRY(rank_barrier(c));
+    std::vector<TermResult> res((size_t)n_terms, TermResult{0.0, 0.0});
+    TRY(pauli_batch(c, n_terms, (const u64*)xmask, (const u64*)ymask, (const u64*)zmask, (const u64*)nmask, res.data()));
+    for (int64_t t = 0; t < n_terms; ++t) {
+        out_re_im[2 * t] = coef[t] * res[t].re;
+        out_re_im[2 * t + 1] = coef[t] * res[t].im;
+    }
+    return QSB_OK;
+}
+
+int qsb_evolve_schedule(qsb_ctx* c, const double* omega, const double* delta, const double* dt_us, int64_t n_steps,
+                        const qsb_eops* eops, double* expectations_out) {
+    if (!c || (n_steps > 0 && (!omega || !delta || !dt_us))) return fail(c, QSB_ERR_INVALID, "NULL argument");
+    if (!c->have_v) return fail(c, QSB_ERR_STATE, "qsb_set_interaction has not been called");
+    const int n_ops = eops ? eops->n_ops : 0;
+    if (n_ops > 0 && !expectations_out) return fail(c, QSB_ERR_INVALID, "expectations_out is NULL");
+    CU(cudaSetDevice(c->device));
+    std::vector<TermResult> res;
+    for (int64_t s = 0; s < n_steps; ++s) {
+        TRY(evolve_segment_impl(c, omega[s], delta[s], dt_us[s], nullptr));
+        for (int o = 0; o < n_ops; ++o) {
+            const qsb_eop& op = eops->ops[o];
+            double val = 0.0;
+            if (op.kind == QSB_EOP_ENERGY) {
+                TRY(energy_impl(c, op.omega, op.delta, &val));
+            } else if (op.kind == QSB_EOP_PAULI) {
+                if (op.term_begin < 0 || op.term_end > eops->n_terms || op.term_begin > op.term_end)
+                    return fail(c, QSB_ERR_INVALID, "e_op %d: bad term range", o);
+                const int64_t nt = op.term_end - op.term_begin;
+                res.assign((size_t)nt, TermResult{0.0, 0.0});
+                TRY(rank_barrier(c));
+                TRY(pauli_batch(c, nt, (const u64*)eops->xmask + op.term_begin, (const u64*)eops->ymask + op.term_begin,
+                                (const u64*)eops->zmask + op.term_begin, (const u64*)eops->nmask + op.term_begin,
+                                res.data()));
+                for (int64_t t = 0; t < nt; ++t) val += eops->coef[op.term_begin + t] * res[t].re;
+            } else {
+                return fail(c, QSB_ERR_INVALID, "e_op %d: unknown kind %d", o, op.kind);
+            }
+            expectations_out[s * n_ops + o] = val;
+        }
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return QSB_OK;
+}
+
+int qsb_norm(qsb_ctx* c, double* out) {
+    if (!c || !out) return fail(c, QSB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    return marginals(c, out, nullptr);
+}
+
+int qsb_energy(qsb_ctx* c, double omega, double delta, double* out) {
+    if (!c || !out) return fail(c, QSB_ERR_INVALID, "NULL argument");
+    if (!c->have_v) return fail(c, QSB_ERR_STATE, "qsb_set_interaction has not been called");
+    CU(cudaSetDevice(c->device));
+    return energy_impl(c, omega, delta, out);
+}
+
+int qsb_number(qsb_ctx* c, double* out) {
+    if (!c || !out) return fail(c, QSB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    return marginals(c, nullptr, out);
+}
+
+int qsb_spins(qsb_ctx* c, double* out) {
+    if (!c || !out) return fail(c, QSB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    const int n = c->n;
+    double tot = 0.0;
+    std::vector<double> num(n);
+    TRY(marginals(c, &tot, num.data()));
+    // <X_q>, <Y_q> as Pauli strings (qse/magnetic.py:157-173)
+    std::vector<u64> xm(2 * n, 0), ym(2 * n, 0), zm(2 * n, 0), nm(2 * n, 0);
+    for (int q = 0; q < n; ++q) {
+        const u64 m = 1ull << (n - 1 - q);
+        xm[q] = m;
+        ym[n + q] = m;
+    }
+    std::vector<TermResult> res(2 * n, TermResult{0.0, 0.0});
+    TRY(rank_barrier(c));
+    TRY(pauli_batch(c, 2 * n, xm.data(), ym.data(), zm.data(), nm.data(), res.data()));
+    for (int q = 0; q < n; ++q) {
+        out[3 * q + 0] = res[q].re;
+        out[3 * q + 1] = res[n + q].re;
+        out[3 * q + 2] = tot - 2.0 * num[q];  // sum p (1 - 2 b), qse/magnetic.py:150-155
+    }
+    return QSB_OK;
+}
+
+int qsb_sisj(qsb_ctx* c, double* out) {
+    if (!c || !out) return fail(c, QSB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    const int n = c->n;
+    const int np = n * (n - 1) / 2;
+    // per pair: ZZ (mode 0, zmask = m_i|m_j) and XX, YY (flip = m_i|m_j)
+    //   s_ij = <Z_iZ_j> + (1/3)(<X_iX_j> + <Y_iY_j>)       (qse/magnetic.py:213-243)
+    std::vector<u64> xm(3 * np, 0), ym(3 * np, 0), zm(3 * np, 0), nm(3 * np, 0);
+    int t = 0;
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j, ++t) {
+            const u64 m = (1ull << (n - 1 - i)) | (1ull << (n - 1 - j));
+            zm[t] = m;
+            xm[np + t] = m;
+            ym[2 * np + t] = m;
+        }
+    std::vector<TermResult> res(3 * np, TermResult{0.0, 0.0});
+    TRY(rank_barrier(c));
+    TRY(pauli_batch(c, 3 * np, xm.data(), ym.data(), zm.data(), nm.data(), res.data()));
+    t = 0;
+    for (int i = 0; i < n; ++i) {
+        out[(size_t)i * n + i] = 1.0;
+        for (int j = i + 1; j < n; ++j, ++t) {
+            const double s = res[t].re + (res[np + t].re + res[2 * np + t].re) / 3.0;
+            out[(size_t)i * n + j] = s;
+            out[(size_t)j * n + i] = s;
+        }
+    }
+    return QSB_OK;
+}
+
+int qsb_probabilities(qsb_ctx* c, double* out) {
+    if (!c || !out) return fail(c, QSB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    // wa is free between calls: use it as the device staging buffer for |psi|^2
+    double* d = reinterpret_cast<double*>(c->wa);
+    prob_kernel<<<grid_for(c, c->dim, 256), 256, 0, c->stream>>>(c->psi, d, c->dim);
+    LAUNCHED(c);
+    TRY(check_launch(c, "prob_kernel"));
+    CU(cudaMemcpyAsync(out, d, c->dim * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return QSB_OK;
+}
+
+int qsb_topk_probs(qsb_ctx* c, int k, uint64_t* idx, double* prob) {
+    if (!c || !idx || !prob || k < 1) return fail(c, QSB_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    const u64 total = c->dim;
+    const u64 kk = std::min<u64>((u64)k, total);
+    // radix select (4 x 16 bits) of the kk-th largest probability of this shard
+    unsigned int* hist = reinterpret_cast<unsigned int*>(c->wb);  // 65536 counters: wb is scratch here
+    std::vector<unsigned int> h(65536);
+    const int grid = grid_for(c, c->dim, 256);
+    u64 prefix = 0, pmask = 0, want = kk;
+    for (int shift = 48; shift >= 0; shift -= 16) {
+        CU(cudaMemsetAsync(hist, 0, 65536 * sizeof(unsigned int), c->stream));
+        radix_hist_kernel<<<grid, 256, 0, c->stream>>>(c->psi, c->dim, prefix, pmask, shift, hist);
+        LAUNCHED(c);
+        TRY(check_launch(c, "radix_hist_kernel"));
+        CU(cudaMemcpyAsync(h.data(), hist, 65536 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        int b = 65535;
+        for (; b >= 0; --b) {
+            if ((u64)h[b] >= want) break;
+            want -= h[b];
+        }
+        if (b < 0) return fail(c, QSB_ERR_STATE, "radix select lost count");
+        prefix |= (u64)b << shift;
+        pmask |= 0xffffull << shift;
+    }
+    // gather everything >= threshold (ties may exceed kk); capacity bounded by the scratch buffer
+    const unsigned int cap = (unsigned int)std::min<u64>(total, std::max<u64>(4 * kk, 1u << 16));
+    // wa holds dim*16 bytes >= cap*16 because cap <= dim
+    u64* d_idx = reinterpret_cast<u64*>(c->wa);
+    double* d_p = reinterpret_cast<double*>(c->wa) + cap;
+    unsigned int* d_count = reinterpret_cast<unsigned int*>(c->slots);
+    CU(cudaMemsetAsync(d_count, 0, sizeof(double), c->stream));
+    gather_ge_kernel<<<grid, 256, 0, c->stream>>>(c->psi, c->dim, prefix, c->rank_bits, d_idx, d_p, d_count, cap);
+    LAUNCHED(c);
+    TRY(check_launch(c, "gather_ge_kernel"));
+    unsigned int count = 0;
+    CU(cudaMemcpyAsync(&count, d_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (count > cap)
+        return fail(c, QSB_ERR_UNSUPPORTED, "top-k: %u amplitudes tie at the k-th probability (capacity %u)", count, cap);
+    std::vector<u64> hi(count);
+    std::vector<double> hp(count);
+    CU(cudaMemcpyAsync(hi.data(), d_idx, count * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(hp.data(), d_p, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemsetAsync(c->slots, 0, sizeof(double), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<std::pair<double, u64>> cand(count);
+    for (unsigned int i = 0; i < count; ++i) cand[i] = {hp[i], hi[i]};
+    auto better = [](const std::pair<double, u64>& a, const std::pair<double, u64>& b) {
+        return a.first > b.first || (a.first == b.first && a.second < b.second);
+    };
+    std::sort(cand.begin(), cand.end(), better);
+    if (cand.size() > kk) cand.resize(kk);
+    if (c->nranks > 1) {
+        // merge the per-shard winners: all-gather kk (p, idx) pairs per rank
+        std::vector<double> mine(2 * kk, -1.0), all(2 * kk * c->nranks);
+        for (size_t i = 0; i < cand.size(); ++i) {
+            mine[2 * i] = cand[i].first;
+            u64 v = cand[i].second;
+            memcpy(&mine[2 * i + 1], &v, sizeof(double));
+        }
+        double* d_m = reinterpret_cast<double*>(c->wa);
+        double* d_a = d_m + 2 * kk;
+        if ((2 * kk * (c->nranks + 1)) * sizeof(double) > c->dim * sizeof(double2))
+            return fail(c, QSB_ERR_UNSUPPORTED, "top-k: k too large for the shard scratch buffer");
+        CU(cudaMemcpyAsync(d_m, mine.data(), mine.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        NC(nccl_api()->AllGather(d_m, d_a, 2 * kk, kNcclFloat64, c->comm, c->stream));
+        CU(cudaMemcpyAsync(all.data(), d_a, all.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        cand.clear();
+        for (size_t i = 0; i < (size_t)kk * c->nranks; ++i) {
+            if (all[2 * i] < 0.0) continue;
+            u64 v;
+            memcpy(&v, &all[2 * i + 1], sizeof(double));
+            cand.push_back({all[2 * i], v});
+        }
+        std::sort(cand.begin(), cand.end(), better);
+    }
+    for (int i = 0; i < k; ++i) {
+        if ((size_t)i < cand.size()) {
+            prob[i] = cand[i].first;
+            idx[i] = cand[i].second;
+        } else {
+            prob[i] = 0.0;
+            idx[i] = ~0ull;
+        }
+    }
+    return QSB_OK;
+}
+
+int qsb_get_metrics(const qsb_ctx* c, qsb_metrics* out) {
+    if (!c || !out) return fail(nullptr, QSB_ERR_INVALID, "NULL argument");
+    *out = c->met;
+    out->hpsi_passes = c->plan.n_pass;
+    out->hpsi_bytes_per_amp = c->plan.bytes_per_amp;
+    out->diag_min = c->diag_min;
+    out->diag_max = c->diag_max;
+    return QSB_OK;
+}
+
+static int flush_l2(qsb_ctx* c) {
+    if (!c->flush_buf) {
+        c->flush_n = (size_t)(192u << 20) / sizeof(double);  // 192 MiB > 126 MB L2
+        CU(cudaMalloc(&c->flush_buf, c->flush_n * sizeof(double)));
+    }
+    flush_kernel<<<c->n_sm * 8, 256, 0, c->stream>>>(c->flush_buf, c->flush_n, 1.0);
+    return check_launch(c, "flush_kernel");
+}
+
+int qsb_time_apply_h(qsb_ctx* c, double omega, double delta, int iters, int do_flush, float* ms_each) {
+    if (!c || !ms_each || iters < 1) return fail(c, QSB_ERR_INVALID, "bad argument");
+    if (!c->have_v) return fail(c, QSB_ERR_STATE, "qsb_set_interaction has not been called");
+    CU(cudaSetDevice(c->device));
+    for (int i = 0; i < iters; ++i) {
+        if (do_flush) TRY(flush_l2(c));
+        TRY(rank_barrier(c));
+        CU(cudaEventRecord(c->ev0, c->stream));
+        TRY(launch_hpsi(c, c->psi, c->wa, omega, delta, false, make_double2(1.0, 0.0), nullptr, nullptr));
+        CU(cudaEventRecord(c->ev1, c->stream));
+        CU(cudaEventSynchronize(c->ev1));
+        CU(cudaEventElapsedTime(&ms_each[i], c->ev0, c->ev1));
+    }
+    TRY(rank_barrier(c));
+    CU(cudaStreamSynchronize(c->stream));
+    return QSB_OK;
+}
+
+int qsb_time_schedule(qsb_ctx* c, const double* omega, const double* delta, const double* dt_us, int64_t n_steps,
+                      float* ms_each) {
+    if (!c || !omega || !delta || !dt_us || !ms_each) return fail(c, QSB_ERR_INVALID, "NULL argument");
+    if (!c->have_v) return fail(c, QSB_ERR_STATE, "qsb_set_interaction has not been called");
+    CU(cudaSetDevice(c->device));
+    for (int64_t s = 0; s < n_steps; ++s) {
+        CU(cudaEventRecord(c->ev0, c->stream));
+        TRY(evolve_segment_impl(c, omega[s], delta[s], dt_us[s], nullptr));
+        CU(cudaEventRecord(c->ev1, c->stream));
+        CU(cudaEventSynchronize(c->ev1));
+        CU(cudaEventElapsedTime(&ms_each[s], c->ev0, c->ev1));
+    }
+    return QSB_OK;
+}
+
+}  // extern "C"

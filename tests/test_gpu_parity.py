@@ -1,0 +1,356 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle
+on the same seeded inputs, against the committed golden vectors of the reference, and — at
+BASELINE.json's full sizes — through size-independent properties.
+
+Tolerances (BASELINE.json north_star): final-state infidelity <= 1e-10, observables <= 1e-9
+absolute (complex128), diagonal / basis indexing bit-exact."""
+import numpy as np
+import pytest
+
+import qse_b200 as qb
+from oracle import rydberg_oracle as orc
+from qse_b200 import lib
+
+pytestmark = pytest.mark.gpu
+
+OMEGA_MAX = 2 * np.pi
+INFID_TOL = 1e-10
+OBS_TOL = 1e-9
+
+
+def random_state(n, seed):
+    rng = np.random.default_rng(seed)
+    psi = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    return psi / np.linalg.norm(psi)
+
+
+def random_positions(n, seed, spacing=6.0):
+    return qb.lattices.random_register(n, spacing, seed=seed).positions
+
+
+# ---- K1: diagonal -------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 5, 9, 12, 15])
+def test_diagonal_bit_exact(n):
+    pos = random_positions(n, 100 + n)
+    v = qb.interaction_matrix(pos)
+    with lib.Engine(n) as eng:
+        eng.set_interaction(v)
+        got = eng.diagonal()
+        m = eng.metrics()
+    want = orc.diagonal_energies(orc.interaction_matrix(pos), n)
+    assert np.array_equal(got, want)  # bit-exact, including the index -> qubit mapping
+    assert m["diag_min"] == want.min() and m["diag_max"] == want.max()
+
+
+def test_diagonal_with_cutoff_pairs(golden):
+    g = golden("interaction.npz")
+    pos = g["3_positions"]  # long chain: far pairs dropped by the 1e-8 cut-off
+    n = pos.shape[0]
+    with lib.Engine(n) as eng:
+        eng.set_interaction(qb.interaction_matrix(pos))
+        assert np.array_equal(eng.diagonal(), orc.diagonal_energies(orc.interaction_matrix(pos), n))
+
+
+# ---- K2/K3: H psi --------------------------------------------------------------------------
+@pytest.mark.parametrize("n,path", [(1, 0), (3, 0), (9, 0), (11, 0), (12, 0), (13, 0), (15, 0), (16, 1),
+                                    (18, 0), (21, 0), (22, 0)])
+def test_apply_h_matches_oracle(n, path):
+    pos = random_positions(n, 7 * n)
+    v = orc.interaction_matrix(pos)
+    e = orc.diagonal_energies(v, n)
+    psi = random_state(n, n)
+    omega, delta = 1.9 * np.pi, -3.7
+    with lib.Engine(n) as eng:
+        eng.set_option("hpsi_path", path)
+        eng.set_interaction(qb.interaction_matrix(pos))
+        eng.set_state(psi)
+        got = eng.apply_h(omega, delta)
+        assert np.array_equal(eng.get_state(), psi)  # input untouched
+    want = orc.apply_hamiltonian(psi, e, n, omega, delta)
+    scale = np.max(np.abs(want))
+    assert np.max(np.abs(got - want)) <= 1e-13 * scale
+
+
+@pytest.mark.parametrize("n", [12, 14, 17, 22, 23])
+def test_tiled_and_untiled_kernels_agree(n):
+    """Two independent kernels (tiled multi-pass vs one-thread-per-amplitude) on one input."""
+    pos = random_positions(n, 3 * n + 1)
+    psi = random_state(n, 50 + n)
+    out = []
+    for path in (0, 1):
+        with lib.Engine(n) as eng:
+            eng.set_option("hpsi_path", path)
+            eng.set_interaction(qb.interaction_matrix(pos))
+            eng.set_state(psi)
+            out.append(eng.apply_h(4.0, 2.5))
+            assert eng.metrics()["hpsi_passes"] == (1 if path else 1 + (n - 12 + 8) // 9)
+    assert np.max(np.abs(out[0] - out[1])) <= 1e-13 * np.max(np.abs(out[1]))
+
+
+# ---- time evolution --------------------------------------------------------------------------
+def sweep(n_values, duration_per_value=1):
+    t = n_values
+    amp = qb.Signal(np.linspace(0, OMEGA_MAX, t), t * duration_per_value)
+    det = qb.Signal(np.linspace(-2 * OMEGA_MAX, 2 * OMEGA_MAX, t), t * duration_per_value)
+    return amp, det
+
+
+def oracle_run(qbits, amp, det, **kw):
+    return orc.calculate(qbits.positions, [(amp.values, amp.duration)], [(det.values, det.duration)], **kw)
+
+
+def test_config1_square_3x3_sweep():
+    """BASELINE config 1: square 3x3 at 0.9 r_b, adiabatic Omega/delta ramp, spins + <s_i s_j>."""
+    qbits = qb.lattices.square(0.9 * qb.blockade_radius(OMEGA_MAX), 3, 3)
+    amp, det = sweep(120, 10)  # 120 values of 10 ns
+    calc = qb.B200(qbits, amp, det)
+    out = calc.calculate()
+    ref = oracle_run(qbits, amp, det, method="eigh")["state"]
+    assert out["state"].shape == (512, 1) and out["state"].dtype == np.complex128
+    assert orc.infidelity(out["state"], ref) <= INFID_TOL
+    assert np.max(np.abs(out["state"] - ref)) <= OBS_TOL  # also phase-exact
+    assert np.max(np.abs(calc.get_spins() - orc.get_spins(ref, 9))) <= OBS_TOL
+    assert np.max(np.abs(calc.get_sij() - orc.get_sisj(ref, 9))) <= OBS_TOL
+    assert np.max(np.abs(calc.get_number_operator() - orc.get_number_operator(ref, 9))) <= OBS_TOL
+    assert calc.spins.shape == (9, 3) and calc.sij.shape == (9, 9)
+    assert abs(np.vdot(calc.statevector, calc.statevector).real - 1) < 1e-12
+    sf = calc.structure_factor_from_sij(3, 3, 1)
+    assert np.max(np.abs(sf - orc.structure_factor_from_sij(3, 3, 1, orc.get_sisj(ref, 9)))) <= OBS_TOL
+    calc.close()
+
+
+def test_single_qubit_closed_form(golden):
+    """tests/qse/calc_test.py:32-53 through the GPU calculator (N = 1, no interaction)."""
+    g = golden("exact_n1.npz")
+    dur = int(g["duration"])
+    for omega, delta, ref_state, closed in zip(g["omega"], g["delta"], g["state"], g["closed_form"]):
+        calc = qb.B200(qb.Qbits(np.zeros((1, 2))), qb.Signal([omega], dur), qb.Signal([delta], dur))
+        psi = calc.calculate()["state"].reshape(-1)
+        assert orc.infidelity(psi, ref_state) < INFID_TOL
+        assert orc.infidelity(psi, closed) < INFID_TOL
+        assert np.max(np.abs(psi - np.exp(1j * delta * dur / 2000) * closed)) < OBS_TOL
+        calc.close()
+
+
+def test_stored_reference_states(golden):
+    """tests/local_tests/results_{myqlm,pulser}.npy: chain(4.0, 4), one 400 ns constant pulse —
+    a single segment with |H| dt ~ 1e3, exercising the sub-stepping."""
+    g = golden("local_tests.npz")
+    dur = int(g["duration"])
+    calc = qb.B200(qb.Qbits(g["positions"]), qb.Signal([float(g["omega"])], dur), qb.Signal([float(g["delta"])], dur))
+    psi = calc.calculate()["state"].reshape(-1)
+    assert calc.metrics["substeps"] > 1
+    assert orc.infidelity(psi, g["myqlm_state"]) < 1e-7
+    assert np.max(np.abs(calc.get_spins() - g["myqlm_spins"])) < 5e-5
+    assert orc.infidelity(psi, g["pulser_state"]) < 1e-4
+    ref = orc.calculate(g["positions"], [([float(g["omega"])], dur)], [([float(g["delta"])], dur)], method="eigh")
+    assert orc.infidelity(psi, ref["state"]) <= INFID_TOL
+    assert np.max(np.abs(psi - ref["state"].reshape(-1))) <= OBS_TOL
+    calc.close()
+
+
+def test_pulser_test_scenario_2x2():
+    """tests/qse_pulser/pulser_test.py:83-106: 2x2 square at 0.9 r_b, 10.01 / 0.12, 400 ns."""
+    qbits = qb.lattices.square(0.9 * qb.blockade_radius(10.01), 2, 2)
+    amp, det = qb.Signal([10.01], 400), qb.Signal([0.12], 400)
+    calc = qb.B200(qbits, amp, det)
+    out = calc.calculate()
+    ref = oracle_run(qbits, amp, det, method="eigh")["state"]
+    assert orc.infidelity(out["state"], ref) <= INFID_TOL
+    calc.close()
+
+
+@pytest.mark.parametrize("name,args", [("triangular", (3, 4)), ("kagome", (2, 2)), ("ring", (10,)), ("chain", (11,))])
+def test_lattice_families_against_exact_propagator(name, args):
+    a = 0.9 * qb.blockade_radius(OMEGA_MAX)
+    qbits = getattr(qb.lattices, name)(a, *args)
+    n = qbits.nqbits
+    amp, det = sweep(25, 4)
+    calc = qb.B200(qbits, amp, det)
+    out = calc.calculate()
+    ref = oracle_run(qbits, amp, det, method="expm_multiply")["state"]
+    assert orc.infidelity(out["state"], ref) <= INFID_TOL
+    assert np.max(np.abs(calc.get_spins() - orc.get_spins(ref, n))) <= OBS_TOL
+    calc.close()
+
+
+@pytest.mark.parametrize("n", [13, 16])
+def test_tiled_path_sweep(n):
+    """Sizes that run the tiled multi-pass kernels with the fused Taylor epilogue."""
+    qbits = qb.lattices.random_register(n, 0.9 * qb.blockade_radius(OMEGA_MAX), seed=n)
+    amp, det = sweep(6, 2)
+    calc = qb.B200(qbits, amp, det)
+    out = calc.calculate()
+    assert calc.metrics["hpsi_passes"] == 2
+    ref = oracle_run(qbits, amp, det, method="expm_multiply")["state"]
+    assert orc.infidelity(out["state"], ref) <= INFID_TOL
+    assert np.max(np.abs(out["state"] - ref)) <= OBS_TOL
+    calc.close()
+
+
+def test_multi_segment_signals_and_tight_lattice():
+    """Signals with several segments of different dt; 0.5 r_b spacing (max |H| dt >> 1)."""
+    qbits = qb.lattices.square(0.5 * qb.blockade_radius(OMEGA_MAX), 3, 2)
+    amp = qb.Signals([qb.Signal(np.linspace(0, OMEGA_MAX, 8), 80), qb.Signal([OMEGA_MAX], 300)])
+    det = qb.Signals([qb.Signal(np.linspace(-5, 5, 8), 80), qb.Signal([5.0], 300)])
+    calc = qb.B200(qbits, amp, det)
+    out = calc.calculate()
+    ref = orc.calculate(qbits.positions, [(s.values, s.duration) for s in amp], [(s.values, s.duration) for s in det],
+                        method="eigh")["state"]
+    assert orc.infidelity(out["state"], ref) <= INFID_TOL
+    assert np.max(np.abs(out["state"] - ref)) <= OBS_TOL
+    calc.close()
+
+
+def test_rk4_method_is_fourth_order():
+    qbits = qb.lattices.square(0.9 * qb.blockade_radius(OMEGA_MAX), 2, 3)
+    amp, det = sweep(50, 1)
+    ref = oracle_run(qbits, amp, det, method="eigh")["state"]
+    calc = qb.B200(qbits, amp, det, method="rk4")
+    out = calc.calculate()
+    assert calc.metrics["hpsi_calls"] == 4 * 50
+    assert orc.infidelity(out["state"], ref) < 1e-9  # RK4 is NOT at the 1e-10 gate in general
+    calc.close()
+
+
+# ---- e_ops ------------------------------------------------------------------------------------
+class _Op:  # duck-typed qse.Operator
+    def __init__(self, operator, indices, nqbits, coef=1.0):
+        self.operator = [operator] * len(indices) if isinstance(operator, str) else operator
+        self.indices, self.nqbits, self.coef = list(indices), nqbits, coef
+
+
+class _Ops:  # duck-typed qse.Operators
+    def __init__(self, operator_list):
+        self.operator_list = operator_list
+
+
+def test_expectations_per_step():
+    qbits = qb.lattices.chain(0.9 * qb.blockade_radius(OMEGA_MAX), 5)
+    n = 5
+    amp, det = sweep(12, 5)
+    calc = qb.B200(qbits, amp, det)
+    h_i, h_f = calc.get_hamiltonian(0.0, -2 * OMEGA_MAX), calc.get_hamiltonian(OMEGA_MAX, 2 * OMEGA_MAX)
+    stagger = _Ops([_Op("Z", [q], n, (-1.0) ** q) for q in range(n)])
+    yz = _Op(["Y", "Z"], [1, 3], n, 0.5)
+    nn = _Op("N", [0, 2], n, 2.0)
+    out = calc.calculate(e_ops=[h_i, h_f, stagger, yz, nn, ("H", 1.0, 0.5)])
+    assert out["expectations"].shape == (12, 6)
+    v = orc.interaction_matrix(qbits.positions)
+    e = orc.diagonal_energies(v, n)
+    fns = [lambda p: orc.energy(p, e, n, 0.0, -2 * OMEGA_MAX),
+           lambda p: orc.energy(p, e, n, OMEGA_MAX, 2 * OMEGA_MAX),
+           lambda p: orc.pauli_expectation(p, n, [((-1.0) ** q, [("Z", q)]) for q in range(n)]).real,
+           lambda p: orc.pauli_expectation(p, n, [(0.5, [("Y", 1), ("Z", 3)])]).real,
+           lambda p: orc.pauli_expectation(p, n, [(2.0, [("N", 0), ("N", 2)])]).real,
+           lambda p: orc.energy(p, e, n, 1.0, 0.5)]
+    ref = oracle_run(qbits, amp, det, method="eigh", e_ops=fns)
+    scale = max(1.0, np.max(np.abs(ref["expectations"])))
+    assert np.max(np.abs(out["expectations"] - ref["expectations"])) <= OBS_TOL * scale
+    assert orc.infidelity(out["state"], ref["state"]) <= INFID_TOL
+    calc.close()
+
+
+# ---- K6/K7: observables -----------------------------------------------------------------------
+def test_observables_against_reference_golden(golden):
+    """Outputs of the reference's own qse.magnetic functions (tests/golden/magnetic.npz)."""
+    g = golden("magnetic.npz")
+    for n in g["sizes"]:
+        n = int(n)
+        psi = g[f"n{n}_state"]
+        assert np.max(np.abs(qb.magnetic.get_spins(psi, n) - g[f"n{n}_spins"])) <= OBS_TOL
+        assert np.max(np.abs(qb.magnetic.get_sisj(psi, n) - g[f"n{n}_sisj"])) <= OBS_TOL
+        assert np.max(np.abs(qb.magnetic.get_number_operator(psi, n) - g[f"n{n}_number"])) <= OBS_TOL
+    for bits in ("1", "00", "001", "101011"):  # tests/qse/magnetic_test.py:46-53 — MSB-first indexing
+        n = len(bits)
+        psi = np.zeros(1 << n, dtype=complex)
+        psi[int(bits, 2)] = 1.0
+        assert np.array_equal(qb.magnetic.get_number_operator(psi, n), np.array([int(c) for c in bits], dtype=float))
+
+
+@pytest.mark.parametrize("n", [10, 14])
+def test_observables_against_oracle(n):
+    psi = random_state(n, 1000 + n)
+    with lib.Engine(n) as eng:
+        eng.set_state(psi)
+        assert abs(eng.norm() - 1.0) < 1e-12
+        assert np.max(np.abs(eng.spins() - orc.get_spins(psi, n))) <= 1e-12
+        assert np.max(np.abs(eng.number() - orc.get_number_operator(psi, n))) <= 1e-12
+        if n <= 10:
+            assert np.max(np.abs(eng.sisj() - orc.get_sisj(psi, n))) <= 1e-12
+        assert np.max(np.abs(eng.probabilities() - np.abs(psi) ** 2)) <= 1e-16
+
+
+def test_topk_bitstrings():
+    n = 14
+    psi = random_state(n, 4)
+    psi[5] = psi[77]  # an exact tie: lower index first
+    p = np.abs(psi) ** 2
+    with lib.Engine(n) as eng:
+        eng.set_state(psi)
+        idx, prob = eng.topk(10)
+    order = np.lexsort((np.arange(p.size), -p))[:10]
+    assert np.array_equal(idx, order.astype(np.uint64))
+    assert np.allclose(prob, p[order], rtol=4e-16, atol=0)  # |c|^2 contracted with FMA on the device
+
+
+# ---- errors ------------------------------------------------------------------------------------
+def test_error_behaviour():
+    with lib.Engine(4) as eng:
+        with pytest.raises(lib.QsbError, match="set_interaction"):
+            eng.apply_h(1.0, 0.0)
+        with pytest.raises(lib.QsbError, match="unknown option"):
+            eng.set_option("nope", 1)
+        with pytest.raises(lib.QsbError, match="overlap"):
+            eng.expect_pauli([1.0], [1], [1], [0], [0])
+    with pytest.raises(Exception, match="same duration"):
+        qb.B200(qb.lattices.chain(5.0, 3), qb.Signal([1.0], 10), qb.Signal([0.0], 20))
+    calc = qb.B200(None, qb.Signal([1.0], 10), qb.Signal([0.0], 10))
+    with pytest.raises(Exception, match="No qbits"):
+        calc.calculate()
+    calc.qbits = qb.lattices.chain(5.0, 3)  # attach later, as README.md:50-52
+    assert calc.calculate()["state"].shape == (8, 1)
+    first = calc.statevector.copy()
+    calc.qbits = qb.lattices.chain(9.0, 4)  # re-attach: H must be rebuilt (reference goes stale)
+    assert calc.calculate()["state"].shape == (16, 1)
+    qbits = qb.Qbits(np.array([[0.0, 0.0], [7.0, 0.0]]), calculator=calc)  # Qbits(calculator=...) hook
+    assert calc.qbits is qbits
+    assert first.shape == (8,)
+    calc.close()
+
+
+# ---- full-size properties (BASELINE config 2: 25 qubits) ----------------------------------------
+def test_full_size_25_qubits_properties():
+    n = 25
+    qbits = qb.lattices.square(0.9 * qb.blockade_radius(OMEGA_MAX), 5, 5)
+    with lib.Engine(n) as eng:
+        eng.set_interaction(qb.interaction_matrix(qbits.positions))
+        assert eng.metrics()["hpsi_passes"] == 3
+        # (1) |0..0> is an eigenvector of the diagonal part: H|0> = (omega/2) sum_q |1_q>
+        eng.reset_state()
+        y = eng.apply_h(2.0, 5.0)
+        nz = np.flatnonzero(y)
+        assert np.array_equal(nz, np.sort(1 << np.arange(n))) and np.all(y[nz] == 1.0)
+        # (2) exact round trip: evolve forward then backward in time returns to the start
+        om, de = np.array([3.0, 6.0]), np.array([-4.0, 2.0])
+        eng.evolve_schedule(om, de, np.array([0.002, 0.002]))
+        assert abs(eng.norm() - 1.0) < 1e-12
+        mid = eng.number()
+        assert np.all(mid > 0) and np.all(mid < 1)
+        eng.evolve_schedule(om[::-1], de[::-1], np.array([-0.002, -0.002]))
+        back = eng.get_state()
+        assert 1.0 - abs(back[0]) ** 2 <= INFID_TOL
+        # (3) energy is real and equals <psi|H|psi> from spins-like reductions on a product state
+        eng.reset_state()
+        assert abs(eng.energy(2.0, 5.0)) < 1e-15
+    # (4) the two independent kernels agree on a random full-size state
+    rng = np.random.default_rng(25)
+    psi = (rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)) / np.sqrt(2.0 ** (n + 1))
+    outs = []
+    for path in (0, 1):
+        with lib.Engine(n) as eng:
+            eng.set_option("hpsi_path", path)
+            eng.set_interaction(qb.interaction_matrix(qbits.positions))
+            eng.set_state(psi)
+            outs.append(eng.apply_h(OMEGA_MAX, -1.5))
+    assert np.max(np.abs(outs[0] - outs[1])) <= 1e-13 * np.max(np.abs(outs[1]))

@@ -1,0 +1,100 @@
+"""Host-side logic of the calculator that needs no GPU: schedule flattening, pulse checks,
+interaction matrix, Pauli mask packing, the structure-factor DFT, the shard plan."""
+import numpy as np
+import pytest
+
+import qse_b200 as qb
+from oracle import rydberg_oracle as orc
+from qse_b200 import calculator as calc_mod
+from qse_b200.distributed import ShardPlan
+
+
+def test_interaction_matrix_bit_identical_to_reference_terms(golden):
+    g = golden("interaction.npz")
+    for c in range(int(g["n_cases"])):
+        v = qb.interaction_matrix(g[f"{c}_positions"])
+        pairs = np.argwhere(v != 0.0)
+        assert np.array_equal(pairs, g[f"{c}_pairs"])
+        assert np.array_equal(v[pairs[:, 0], pairs[:, 1]], g[f"{c}_coefs"])
+        assert np.array_equal(v, orc.interaction_matrix(g[f"{c}_positions"]))
+
+
+def test_flatten_schedule_takes_dt_from_amplitude_only():
+    amp = qb.Signals([qb.Signal(np.linspace(0, 1, 5), 20), qb.Signal([3.0], 400)])
+    det = qb.Signals([qb.Signal(np.linspace(-1, 1, 5), 10), qb.Signal([0.5], 410)])
+    calc_mod._check_pulses(amp, det)  # total durations equal (420), per-segment ones are not checked
+    om, de, dt = qb.flatten_schedule(amp, det)
+    assert np.array_equal(om, [0, 0.25, 0.5, 0.75, 1.0, 3.0])
+    assert np.array_equal(dt, [0.004] * 5 + [0.4])
+    o2, d2, t2 = orc.flatten_schedule([(s.values, s.duration) for s in amp], [(s.values, s.duration) for s in det])
+    assert np.array_equal(om, o2) and np.array_equal(de, d2) and np.array_equal(dt, t2)
+
+
+def test_check_pulses_messages():
+    s = qb.Signal
+    with pytest.raises(Exception, match="must have the same duration"):
+        calc_mod._check_pulses(qb.Signals([s([1.0], 10)]), qb.Signals([s([1.0], 20)]))
+    with pytest.raises(Exception, match="same number of signals"):
+        calc_mod._check_pulses(qb.Signals([s([1.0], 10), s([1.0], 10)]), qb.Signals([s([1.0], 20)]))
+    with pytest.raises(Exception, match="same amount of values"):
+        calc_mod._check_pulses(qb.Signals([s([1.0, 2.0], 10)]), qb.Signals([s([1.0], 10)]))
+
+
+def test_pauli_masks_msb_first():
+    assert calc_mod._pauli_masks(["X"], [0], 3) == (0b100, 0, 0, 0)
+    assert calc_mod._pauli_masks(["Y", "Z"], [2, 4], 5) == (0, 0b00100, 0b00001, 0)
+    assert calc_mod._pauli_masks(["N", "N"], [0, 5], 6) == (0, 0, 0, 0b100001)
+    with pytest.raises(Exception, match="must be one of"):
+        calc_mod._pauli_masks(["Q"], [0], 2)
+    with pytest.raises(Exception, match="only once"):
+        calc_mod._pauli_masks(["X", "Z"], [1, 1], 2)
+
+
+def test_structure_factor_matches_oracle_dft():
+    rng = np.random.default_rng(5)
+    l1, l2, l3 = 3, 2, 2
+    n = l1 * l2 * l3
+    s = rng.normal(size=(n, n))
+    s = s + s.T
+    q = qb.Qbits(np.zeros((n, 3)))
+    got = qb.magnetic.structure_factor_from_sij(l1, l2, l3, q, s)
+    assert got.shape == (l1, l2, l3)
+    assert np.max(np.abs(got - orc.structure_factor_from_sij(l1, l2, l3, s))) < 1e-13
+
+
+def test_shard_plan():
+    plan = ShardPlan(5, 4)
+    assert (plan.p, plan.nl, plan.local_dim) == (2, 3, 8)
+    assert plan.owner(0b10110) == 0b10 and plan.local_index(0b10110) == 0b110
+    assert plan.partner(0b10, 0) == 0b00 and plan.partner(0b10, 1) == 0b11
+    assert plan.shard_slice(3) == slice(24, 32)
+    v = np.zeros((5, 5))
+    v[0, 1] = 7.0
+    assert plan.rank_diagonal_offset(0b11, v) == 7.0 and plan.rank_diagonal_offset(0b10, v) == 0.0
+    with pytest.raises(ValueError):
+        ShardPlan(5, 3)
+
+
+def test_sharded_algorithm_reproduces_full_hpsi():
+    """The shard decomposition libqsb implements, restated with numpy shards against the oracle:
+    local H psi with rank-dependent diagonal + (omega/2) * partner shard per sharded qubit."""
+    rng = np.random.default_rng(11)
+    n, world = 6, 4
+    plan = ShardPlan(n, world)
+    pos = rng.uniform(0, 20, size=(n, 2))
+    v = orc.interaction_matrix(pos)
+    e = orc.diagonal_energies(v, n)
+    psi = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    omega, delta = 2.3, -1.1
+    full = orc.apply_hamiltonian(psi, e, n, omega, delta)
+    for r in range(world):
+        sl = plan.shard_slice(r)
+        local = psi[sl]
+        k = np.arange(plan.local_dim)
+        pop = np.array([bin(int(x)).count("1") for x in k]) + plan.rank_popcount(r)
+        y = (e[sl] - delta * pop) * local
+        for q in range(plan.nl):
+            y = y + 0.5 * omega * local[k ^ (1 << q)]
+        for g in plan.sharded_qubits():
+            y = y + 0.5 * omega * psi[plan.shard_slice(plan.partner(r, g))]
+        assert np.max(np.abs(y - full[sl])) < 1e-12
