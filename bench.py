@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — the measurement contract for the Rydberg sweep hot path.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3            # this repo's arm (default)
+    python bench.py --impl reference --steps 20 --warmup 3    # the CPU arm (oracle port, host cores)
+    torchrun --nproc-per-node P bench.py --gpus P ...          # one rank per GPU, sharded state
+
+A "step" is one sweep step: psi <- exp(-i H(omega_s, delta_s) dt) psi (one signal value of
+Qutip.calculate's loop, qse/calc/qutip.py:42-45).  Workload (BASELINE config 2):
+square lattice 5x5 (25 qubits, 2^25 amplitudes per GPU) at 0.9 r_b(Omega_max = 2 pi), adiabatic
+ramp Omega: 0 -> Omega_max, delta: -2 Omega_max -> +2 Omega_max, 1 ns per value.  With P GPUs the
+per-GPU shard stays 2^25 amplitudes (weak scaling): 25 + log2(P) qubits on a 5x5 / 2x13 / 3x9 /
+4x7 rectangle of the same square lattice.
+
+`value` = H psi HBM GB/s in the 40 B/amplitude currency of SURVEY.md §8(d) sustained over the
+timed sweep steps: 40 B * 2^N * (number of H psi applied) / time, whole job.  `steps_per_s` is the
+other half of BASELINE.json's metric.  One JSON line on stdout (rank 0).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+OMEGA_MAX = 2 * np.pi
+BYTES_PER_AMP = 40.0  # 16 (read psi) + 8 (read E_int) + 16 (write y): SURVEY.md §8(d)
+SHAPES = {25: (5, 5), 26: (2, 13), 27: (3, 9), 28: (4, 7), 20: (4, 5), 22: (2, 11), 24: (4, 6), 16: (4, 4),
+          12: (3, 4), 9: (3, 3), 30: (5, 6)}
+
+
+def workload(n_qubits: int, n_values: int):
+    import qse_b200 as qb
+
+    a = 0.9 * qb.blockade_radius(OMEGA_MAX)
+    qbits = qb.lattices.square(a, *SHAPES[n_qubits])
+    amp = qb.Signal(np.linspace(0.0, OMEGA_MAX, n_values), n_values)  # 1 ns per value
+    det = qb.Signal(np.linspace(-2 * OMEGA_MAX, 2 * OMEGA_MAX, n_values), n_values)
+    return qbits, amp, det
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C port on the host cores (the reference itself is Python + QuTiP, absent)
+# --------------------------------------------------------------------------------------------
+def cpu_port_run(n_qubits: int, steps: int, warmup: int, budget_s: float):
+    """Time the C restatement on the same workload.  Returns (gbs, steps_per_s, info)."""
+    from oracle import c_port
+    from oracle import rydberg_oracle as orc
+
+    qbits, amp, det = workload(n_qubits, warmup + steps)
+    v = orc.interaction_matrix(qbits.positions)
+    e = c_port.build_diagonal(v, n_qubits)
+    om, de, dt = orc.flatten_schedule([(amp.values, amp.duration)], [(det.values, det.duration)])
+    cores = c_port.threads()
+    psi = np.zeros(1 << n_qubits, dtype=np.complex128)
+    psi[0] = 1.0
+    # probe one H psi to decide what a bounded "step" can be
+    t0 = time.perf_counter()
+    c_port.apply_h(psi, e, n_qubits, om[-1], de[-1])
+    t_probe = time.perf_counter() - t0
+    full_steps = 10.0 * t_probe * (steps + warmup) <= budget_s
+    amps = float(1 << n_qubits)
+    if full_steps:
+        psi, _ = c_port.evolve_schedule(psi, e, n_qubits, om[:warmup], de[:warmup], dt[:warmup])
+        t0 = time.perf_counter()
+        psi, n_hpsi = c_port.evolve_schedule(psi, e, n_qubits, om[warmup:], de[warmup:], dt[warmup:])
+        t = time.perf_counter() - t0
+        sample = f"{steps} full sweep steps of the {n_qubits}-qubit workload ({n_hpsi} H psi), after {warmup} warm-up steps"
+        return BYTES_PER_AMP * amps * n_hpsi / t / 1e9, steps / t, {
+            "cores": cores, "sample": sample, "n_hpsi": n_hpsi, "seconds": t, "ms_per_step": 1e3 * t / steps}
+    # too slow for whole steps: each step = ONE H psi application of the same workload
+    rng = np.random.default_rng(1234)
+    psi = rng.standard_normal(1 << n_qubits) + 1j * rng.standard_normal(1 << n_qubits)
+    psi /= np.linalg.norm(psi)
+    for _ in range(warmup):
+        c_port.apply_h(psi, e, n_qubits, om[-1], de[-1])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        c_port.apply_h(psi, e, n_qubits, om[-1], de[-1])
+    t = time.perf_counter() - t0
+    sample = (f"{steps} single H psi applications of the {n_qubits}-qubit workload (a full sweep step is ~9 of them; "
+              f"whole steps would exceed the {budget_s:.0f} s budget)")
+    return BYTES_PER_AMP * amps * steps / t / 1e9, steps / t / 9.0, {
+        "cores": cores, "sample": sample, "n_hpsi": steps, "seconds": t, "ms_per_step": 1e3 * t / steps}
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    n = 25 + (world.bit_length() - 1)
+    gbs, sps, info = cpu_port_run(n, args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": "hpsi_hbm_gbs_in_sweep", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
+        "steps_per_s": sps,
+        "config": {"workload": f"square {SHAPES[n][0]}x{SHAPES[n][1]} ({n} qubits) adiabatic sweep, complex128, 1 ns steps",
+                   "arm": "CPU port of the reference path (oracle/c/rydberg_ref.c, OpenMP): QuTiP is not installable here"},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------
+def run_b200(args, rank: int, world: int, local_rank: int):
+    import torch
+
+    import qse_b200 as qb
+    from qse_b200 import lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    p = world.bit_length() - 1
+    n = args.qubits + p
+    K, W = args.steps, args.warmup
+    qbits, amp, det = workload(n, W + K)
+    om, de, dt = qb.flatten_schedule(qb.Signals([amp]), qb.Signals([det]))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    uid = None
+    if world > 1:
+        from qse_b200 import distributed as qdist
+
+        uid = qdist.broadcast_unique_id()
+    eng = lib.Engine(n, device=local_rank, rank=rank, nranks=world, nccl_uid=uid)
+    eng.set_interaction(qb.interaction_matrix(qbits.positions))
+    amps_total = float(1 << n)
+
+    # ---- value: device-resident sweep ---------------------------------------------------
+    eng.reset_state()
+    eng.evolve_schedule(om[:W], de[:W], dt[:W])  # W untimed warm-up steps
+    m0 = eng.metrics()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    step_ms = eng.time_schedule(om[W:], de[W:], dt[W:])  # CUDA events on the library's stream, per step
+    barrier()
+    t_wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    m1 = eng.metrics()
+    n_hpsi = m1["hpsi_calls"] - m0["hpsi_calls"]
+    launches = m1["kernel_launches"] - m0["kernel_launches"]
+    t_dev = float(np.sum(step_ms)) * 1e-3
+    t_region = max(t_wall, t_dev)
+    if dist is not None:
+        from qse_b200 import distributed as qdist
+
+        t_region = qdist.max_over_ranks(t_region)
+    value = BYTES_PER_AMP * amps_total * n_hpsi / t_region / 1e9
+    norm = eng.norm()
+
+    # ---- roofline leg: H psi alone, CUDA events around each application ----------------------
+    hp_ms = eng.time_apply_h(float(om[-1]), float(de[-1]), 12, False)[2:]
+    if dist is not None:
+        hp_ms = np.array([qdist.max_over_ranks(float(np.median(hp_ms)))])
+    t_hpsi = float(np.median(hp_ms)) * 1e-3
+    peak, peak_src = measured_peaks()
+    achieved = BYTES_PER_AMP * amps_total / t_hpsi / 1e9 / world  # per GPU
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get(str(n if world == 1 else -1))
+    met = eng.metrics()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": f"H psi = {met['hpsi_passes']} launches of hpsi_tile_kernel (passes), timed as a group",
+                "algorithmic_bytes_per_launch_group": BYTES_PER_AMP * amps_total / world,
+                "planned_hbm_bytes_per_amp": met["hpsi_bytes_per_amp"],
+                "hpsi_ms": t_hpsi * 1e3,
+                "in_sweep": {"achieved": value / world, "frac": value / world / peak,
+                             "note": "fused Taylor step: same 40 B/amp currency, region time / number of H psi"}}
+
+    # ---- e2e: the plugin call with host buffers -------------------------------------------
+    eng.close()
+    k_amp = qb.Signal(amp.values[W:], K)
+    k_det = qb.Signal(det.values[W:], K)
+    calc = qb.B200(qbits, qb.Signal(amp.values[:W], W), qb.Signal(det.values[:W], W), device=local_rank,
+                   return_state=(world == 1))
+    calc.calculate()  # warm-up: builds the context and the diagonal
+    calc.amplitude, calc.detuning = qb.Signals([k_amp]), qb.Signals([k_det])
+    barrier()
+    t0 = time.perf_counter()
+    out = calc.calculate()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    if dist is not None:
+        t_e2e = qdist.max_over_ranks(t_e2e)
+    e2e_hpsi = calc.metrics["hpsi_calls"]
+    e2e_val = BYTES_PER_AMP * amps_total * e2e_hpsi / t_e2e / 1e9
+    state_bytes = out["state"].nbytes if "state" in out else 0
+    h2d = (3 * 8 * K) / K
+    d2h = (state_bytes / world + n * 3 * 8) / K
+    e2e_launches = calc.metrics["kernel_launches"]
+    calc.close()
+
+    line = {
+        "metric": "hpsi_hbm_gbs_in_sweep", "value": value, "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * t_region / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "complex128", "data": "synthetic",
+        "steps_per_s": K / t_region,
+        "config": {"workload": f"square {SHAPES[n][0]}x{SHAPES[n][1]} ({n} qubits) adiabatic sweep, complex128, 1 ns steps",
+                   "amplitudes_per_gpu": 1 << (n - p), "hpsi_per_step": n_hpsi / K,
+                   "l2": "inputs larger than L2 (state 512 MiB/GPU + diagonal 256 MiB vs 126 MB L2); no flush",
+                   "parallelism": f"state sharded by top {p} qubit(s) over {world} GPU(s)", "stepper": "taylor tol 1e-14"},
+        "roofline": roofline,
+        "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps_per_s": K / t_e2e, "seconds": t_e2e,
+                "note": "qse_b200.B200.calculate() for the K timed values: schedule upload, sweep, final state "
+                        "copied back to a host ndarray, spins reduced on device"},
+        "gpu_launches": int(launches),
+        "e2e_gpu_launches": int(e2e_launches),
+        "clocks": clocks,
+        "norm_after_sweep": norm,
+        "device_event_ms_per_step": float(np.mean(step_ms)),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        gbs, sps, info = cpu_port_run(n, 4, 1, budget_s=40.0)
+        line["cpu_baseline"] = {"value": gbs, "unit": "GB/s", "cores": info["cores"], "kind": "port",
+                                "sample": info["sample"], "steps_per_s": sps}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--qubits", type=int, default=25, help="qubits per 1-GPU shard (default: BASELINE config 2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3  # timing rules: W >= 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
