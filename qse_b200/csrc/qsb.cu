@@ -57,6 +57,8 @@ struct qsb_ctx {
     // measurement
     double* flush_buf = nullptr;
     size_t flush_n = 0;
+    unsigned char* topk_buf = nullptr;  // radix histogram + candidate lists (lazily allocated)
+    size_t topk_bytes = 0;
     qsb_metrics met;
     char err[512] = "";
 };
@@ -624,6 +626,7 @@ int qsb_destroy(qsb_ctx* c) {
     cudaFree(c->part);
     cudaFree(c->slots);
     cudaFree(c->flush_buf);
+    cudaFree(c->topk_buf);
     if (c->h_slots) cudaFreeHost(c->h_slots);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -909,8 +912,19 @@ int qsb_topk_probs(qsb_ctx* c, int k, uint64_t* idx, double* prob) {
     CU(cudaSetDevice(c->device));
     const u64 total = c->dim;
     const u64 kk = std::min<u64>((u64)k, total);
+    // scratch: 65536 counters | cap x (idx, p) candidates | all-gather staging of 2*kk doubles per rank
+    const unsigned int cap = (unsigned int)std::min<u64>(total, std::max<u64>(4 * kk, 1u << 16));
+    const size_t hist_bytes = 65536 * sizeof(unsigned int);
+    const size_t need = hist_bytes + (size_t)cap * 16 + (size_t)2 * kk * (c->nranks + 1) * sizeof(double);
+    if (need > c->topk_bytes) {
+        cudaFree(c->topk_buf);
+        c->topk_buf = nullptr;
+        c->topk_bytes = 0;
+        CU(cudaMalloc(&c->topk_buf, need));
+        c->topk_bytes = need;
+    }
     // radix select (4 x 16 bits) of the kk-th largest probability of this shard
-    unsigned int* hist = reinterpret_cast<unsigned int*>(c->wb);  // 65536 counters: wb is scratch here
+    unsigned int* hist = reinterpret_cast<unsigned int*>(c->topk_buf);
     std::vector<unsigned int> h(65536);
     const int grid = grid_for(c, c->dim, 256);
     u64 prefix = 0, pmask = 0, want = kk;
@@ -931,10 +945,8 @@ int qsb_topk_probs(qsb_ctx* c, int k, uint64_t* idx, double* prob) {
         pmask |= 0xffffull << shift;
     }
     // gather everything >= threshold (ties may exceed kk); capacity bounded by the scratch buffer
-    const unsigned int cap = (unsigned int)std::min<u64>(total, std::max<u64>(4 * kk, 1u << 16));
-    // wa holds dim*16 bytes >= cap*16 because cap <= dim
-    u64* d_idx = reinterpret_cast<u64*>(c->wa);
-    double* d_p = reinterpret_cast<double*>(c->wa) + cap;
+    u64* d_idx = reinterpret_cast<u64*>(c->topk_buf + hist_bytes);
+    double* d_p = reinterpret_cast<double*>(c->topk_buf + hist_bytes) + cap;
     unsigned int* d_count = reinterpret_cast<unsigned int*>(c->slots);
     CU(cudaMemsetAsync(d_count, 0, sizeof(double), c->stream));
     gather_ge_kernel<<<grid, 256, 0, c->stream>>>(c->psi, c->dim, prefix, c->rank_bits, d_idx, d_p, d_count, cap);
@@ -966,10 +978,8 @@ int qsb_topk_probs(qsb_ctx* c, int k, uint64_t* idx, double* prob) {
             u64 v = cand[i].second;
             memcpy(&mine[2 * i + 1], &v, sizeof(double));
         }
-        double* d_m = reinterpret_cast<double*>(c->wa);
+        double* d_m = reinterpret_cast<double*>(c->topk_buf + hist_bytes + (size_t)cap * 16);
         double* d_a = d_m + 2 * kk;
-        if ((2 * kk * (c->nranks + 1)) * sizeof(double) > c->dim * sizeof(double2))
-            return fail(c, QSB_ERR_UNSUPPORTED, "top-k: k too large for the shard scratch buffer");
         CU(cudaMemcpyAsync(d_m, mine.data(), mine.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         NC(nccl_api()->AllGather(d_m, d_a, 2 * kk, kNcclFloat64, c->comm, c->stream));
         CU(cudaMemcpyAsync(all.data(), d_a, all.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
