@@ -90,3 +90,35 @@ QSB_DEV void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+
+// ---- extra primitives for the warp-specialised pipeline ------------------------------------
+QSB_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+QSB_DEV void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+QSB_DEV unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// L2-only loads (no L1 allocation): data another SM wrote earlier in the same kernel
+QSB_DEV double2 ldcg2(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+// read-only 8-byte load kept in program order (the compiler sinks plain __ldg loads to their use)
+QSB_DEV double ldnc1(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+QSB_DEV double2 ldg2_volatile(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}

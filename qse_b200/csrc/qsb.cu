@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "hpsi.cuh"
+#include "hpsi_ws.cuh"
 #include "nccl_dl.h"
 #include "observe.cuh"
 
@@ -43,6 +44,13 @@ struct qsb_ctx {
     double* h_slots = nullptr;
     size_t slots_n = 0;
     HpsiPlan plan;
+    // warp-specialised super-block path (hpsi_ws.cuh)
+    int path = 0;       // 0 auto (ws when N_local >= 13), 1 untiled, 2 one launch per tile-bit group
+    int sb_bits = 19;   // log2 of the L2-resident super-block (2 x 20 MiB in flight: measured best on B200)
+    unsigned int* tickets = nullptr;        // one work counter per launch of an H psi
+    unsigned long long* sb_done = nullptr;  // per super-block completion counters (cumulative)
+    unsigned long long ws_epoch = 0;
+    int ws_sbits_active = -1;  // super-block size the completion counters were accumulated with
     // options
     double tol = 1e-14, theta_max = 3.0;
     int max_terms = 64, fixed_terms = 0, force_flat = 0;
@@ -137,6 +145,88 @@ static const double2* peer_of(qsb_ctx* c, const double2* x, int partner) {
     return nullptr;
 }
 
+struct WsPlan {
+    int sbits;
+    PassGeom inner;
+    int n_plain;
+    PassGeom plain[6];
+    double bytes_per_amp;
+};
+static WsPlan make_ws_plan(int nl, int sb_bits) {
+    WsPlan w{};
+    w.sbits = std::min(nl, std::min(sb_bits, kTileBits + 9));
+    const int hb = w.sbits - kTileBits;
+    w.inner = PassGeom{kTileBits - hb, hb, kTileBits};
+    w.bytes_per_amp = 40.0;
+    int rem = nl - w.sbits;
+    const int max_hb = kTileBits - 3;
+    const int extra = (rem + max_hb - 1) / max_hb;
+    int pos = w.sbits;
+    for (int i = 0; i < extra; ++i) {
+        const int h = (rem + (extra - i) - 1) / (extra - i);
+        w.plain[w.n_plain++] = PassGeom{kTileBits - h, h, pos};
+        w.bytes_per_amp += 48.0;
+        pos += h;
+        rem -= h;
+    }
+    return w;
+}
+
+// warp-specialised path: one fused launch over L2-resident super-blocks + plain launches for the
+// index bits above the super-block (hpsi_ws.cuh)
+static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, double omega, double delta, bool fuse,
+                          double2 scale, double2* acc, double* norm_slot, const double2* const* peers) {
+    const WsPlan w = make_ws_plan(c->nl, c->sb_bits);
+    const u64 n_tiles = c->dim >> kTileBits;
+    const int grid = (int)std::min<u64>(n_tiles, (u64)c->n_sm);
+    CU(cudaMemsetAsync(c->tickets, 0, 16 * sizeof(unsigned int), c->stream));
+    HpsiWs a{};
+    a.x = x;
+    a.y = y;
+    a.eint = c->eint;
+    for (int g = 0; g < kMaxPeers; ++g) a.peer[g] = peers[g];
+    a.n_peer = c->p;
+    a.half_omega = 0.5 * omega;
+    a.delta = delta;
+    a.scale = fuse ? scale : make_double2(1.0, 0.0);
+    a.nl = c->nl;
+    a.pop_rank = c->pop_rank;
+    a.done = c->sb_done;
+    a.n_tiles = n_tiles;
+    for (int i = 0; i <= w.n_plain; ++i) {
+        const bool last = (i == w.n_plain);
+        a.fused = (i == 0);
+        const PassGeom g = (i == 0) ? w.inner : w.plain[i - 1];
+        a.sbits = w.sbits;
+        a.lb = g.lb;
+        a.hb = g.hb;
+        a.hb0 = g.hb0;
+        a.last = last ? 1 : 0;
+        a.acc = (fuse && last) ? acc : nullptr;
+        a.norm_part = (fuse && last && norm_slot) ? c->part : nullptr;
+        a.ticket = c->tickets + i;
+        if (i == 0) {
+            if (c->ws_sbits_active != w.sbits) {
+                // the counters are cumulative per super-block: a new block size starts a new count
+                CU(cudaMemsetAsync(c->sb_done, 0, ((size_t)(c->dim >> 13) + 1) * sizeof(unsigned long long), c->stream));
+                c->ws_epoch = 0;
+                c->ws_sbits_active = w.sbits;
+            }
+            c->ws_epoch++;
+            a.done_target = c->ws_epoch << (w.sbits - kTileBits);
+        }
+        hpsi_ws_kernel<<<grid, kWsThreads, kWsSmemBytes, c->stream>>>(a);
+        LAUNCHED(c);
+        TRY(check_launch(c, "hpsi_ws_kernel"));
+    }
+    if (fuse && norm_slot) {
+        finalize_sum_kernel<<<1, 256, 0, c->stream>>>(c->part, grid, norm_slot);
+        LAUNCHED(c);
+        TRY(check_launch(c, "finalize_sum_kernel"));
+    }
+    return QSB_OK;
+}
+
 // y <- scale * H(omega, delta) x   [fuse: acc += y (acc may be null), *norm_slot <- |y|^2 of this shard]
 static int launch_hpsi(qsb_ctx* c, const double2* x, double2* y, double omega, double delta, bool fuse,
                        double2 scale, double2* acc, double* norm_slot) {
@@ -182,6 +272,7 @@ static int launch_hpsi(qsb_ctx* c, const double2* x, double2* y, double omega, d
         }
         return check_launch(c, "finalize_sum_kernel");
     }
+    if (c->path == 0 && c->nl > kTileBits) return launch_hpsi_ws(c, x, y, omega, delta, fuse, scale, acc, norm_slot, peers);
     const u64 n_tiles = c->dim >> kTileBits;
     const int grid = (int)std::min<u64>(n_tiles, (u64)c->n_sm);
     for (int i = 0; i < c->plan.n_pass; ++i) {
@@ -582,6 +673,13 @@ int qsb_create_sharded(int n_qubits, int device, int rank, int nranks, const voi
         CUB(cudaFuncSetAttribute(hpsi_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
         CUB(cudaFuncSetAttribute(hpsi_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
         CUB(cudaFuncSetAttribute(hpsi_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+        CUB(cudaFuncSetAttribute(hpsi_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes));
+        CUB(cudaMalloc(&c->tickets, 16 * sizeof(unsigned int)));
+        {
+            const size_t n_done = (size_t)(c->dim >> 13) + 1;
+            CUB(cudaMalloc(&c->sb_done, n_done * sizeof(unsigned long long)));
+            CUB(cudaMemset(c->sb_done, 0, n_done * sizeof(unsigned long long)));
+        }
 #undef CUB
         c->plan = make_plan(c->nl, false);
         if (nranks > 1) rc = setup_comm(c, nccl_uid);
@@ -627,6 +725,8 @@ int qsb_destroy(qsb_ctx* c) {
     cudaFree(c->slots);
     cudaFree(c->flush_buf);
     cudaFree(c->topk_buf);
+    cudaFree(c->tickets);
+    cudaFree(c->sb_done);
     if (c->h_slots) cudaFreeHost(c->h_slots);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -657,8 +757,13 @@ int qsb_set_option(qsb_ctx* c, const char* key, double value) {
         if (value < 0 || value > 4000) return fail(c, QSB_ERR_INVALID, "fixed_terms out of range");
         c->fixed_terms = (int)value;
     } else if (!strcmp(key, "hpsi_path")) {
-        c->force_flat = value != 0.0;
+        if (value != 0.0 && value != 1.0 && value != 2.0) return fail(c, QSB_ERR_INVALID, "hpsi_path must be 0, 1 or 2");
+        c->path = (int)value;
+        c->force_flat = c->path == 1;
         c->plan = make_plan(c->nl, c->force_flat);
+    } else if (!strcmp(key, "sb_bits")) {
+        if (value < 13 || value > 21) return fail(c, QSB_ERR_INVALID, "sb_bits must be in 13..21");
+        c->sb_bits = (int)value;
     } else {
         return fail(c, QSB_ERR_INVALID, "unknown option '%s'", key);
     }
@@ -1010,6 +1115,11 @@ int qsb_get_metrics(const qsb_ctx* c, qsb_metrics* out) {
     *out = c->met;
     out->hpsi_passes = c->plan.n_pass;
     out->hpsi_bytes_per_amp = c->plan.bytes_per_amp;
+    if (c->path == 0 && c->nl > kTileBits) {
+        const WsPlan w = make_ws_plan(c->nl, c->sb_bits);
+        out->hpsi_passes = 1 + w.n_plain;  // launches; the first one fuses two sub-passes through L2
+        out->hpsi_bytes_per_amp = w.bytes_per_amp;
+    }
     out->diag_min = c->diag_min;
     out->diag_max = c->diag_max;
     return QSB_OK;

@@ -72,19 +72,50 @@ def test_apply_h_matches_oracle(n, path):
 
 
 @pytest.mark.parametrize("n", [12, 14, 17, 22, 23])
-def test_tiled_and_untiled_kernels_agree(n):
-    """Two independent kernels (tiled multi-pass vs one-thread-per-amplitude) on one input."""
+def test_independent_kernels_agree(n):
+    """Three independent kernels on one input: warp-specialised super-block path (0), one
+    launch per tile-bit group (2), one thread per amplitude (1)."""
     pos = random_positions(n, 3 * n + 1)
     psi = random_state(n, 50 + n)
-    out = []
-    for path in (0, 1):
+    out = {}
+    for path in (0, 2, 1):
         with lib.Engine(n) as eng:
             eng.set_option("hpsi_path", path)
             eng.set_interaction(qb.interaction_matrix(pos))
             eng.set_state(psi)
-            out.append(eng.apply_h(4.0, 2.5))
-            assert eng.metrics()["hpsi_passes"] == (1 if path else 1 + (n - 12 + 8) // 9)
+            out[path] = eng.apply_h(4.0, 2.5)
+            passes = eng.metrics()["hpsi_passes"]
+            if path == 2:
+                assert passes == 1 + (n - 12 + 8) // 9
+            elif path == 1:
+                assert passes == 1
+            else:
+                assert passes == (1 if n <= 19 else 2)
     assert np.max(np.abs(out[0] - out[1])) <= 1e-13 * np.max(np.abs(out[1]))
+    assert np.max(np.abs(out[2] - out[1])) <= 1e-13 * np.max(np.abs(out[1]))
+
+
+@pytest.mark.parametrize("n,sb", [(13, 13), (15, 13), (17, 13), (17, 15), (19, 16), (22, 14), (22, 19), (23, 21)])
+def test_super_block_schedules(n, sb):
+    """Many small super-blocks stress the in-kernel A -> B dependency counters; every schedule
+    must give the same H psi (checked against the untiled kernel), twice in a row (epochs)."""
+    pos = random_positions(n, 5 * n + sb)
+    psi = random_state(n, 70 + n)
+    with lib.Engine(n) as eng:
+        eng.set_interaction(qb.interaction_matrix(pos))
+        eng.set_state(psi)
+        eng.set_option("hpsi_path", 1)
+        want = eng.apply_h(4.0, 2.5)
+        eng.set_option("hpsi_path", 0)
+        eng.set_option("sb_bits", sb)
+        for _ in range(3):
+            got = eng.apply_h(4.0, 2.5)
+            assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+        # changing the block size mid-life restarts the completion counters
+        eng.set_option("sb_bits", 13 if sb != 13 else 14)
+        got = eng.apply_h(4.0, 2.5)
+        assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+        assert eng.time_apply_h(4.0, 2.5, 4).shape == (4,)
 
 
 # ---- time evolution --------------------------------------------------------------------------
@@ -181,7 +212,7 @@ def test_tiled_path_sweep(n):
     amp, det = sweep(6, 2)
     calc = qb.B200(qbits, amp, det)
     out = calc.calculate()
-    assert calc.metrics["hpsi_passes"] == 2
+    assert calc.metrics["hpsi_passes"] == 1  # one fused launch (two sub-passes through L2)
     ref = oracle_run(qbits, amp, det, method="expm_multiply")["state"]
     assert orc.infidelity(out["state"], ref) <= INFID_TOL
     assert np.max(np.abs(out["state"] - ref)) <= OBS_TOL
@@ -325,7 +356,7 @@ def test_full_size_25_qubits_properties():
     qbits = qb.lattices.square(0.9 * qb.blockade_radius(OMEGA_MAX), 5, 5)
     with lib.Engine(n) as eng:
         eng.set_interaction(qb.interaction_matrix(qbits.positions))
-        assert eng.metrics()["hpsi_passes"] == 3
+        assert eng.metrics()["hpsi_passes"] == 2  # fused super-block launch + one plain launch
         # (1) |0..0> is an eigenvector of the diagonal part: H|0> = (omega/2) sum_q |1_q>
         eng.reset_state()
         y = eng.apply_h(2.0, 5.0)
@@ -347,7 +378,7 @@ def test_full_size_25_qubits_properties():
     rng = np.random.default_rng(25)
     psi = (rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)) / np.sqrt(2.0 ** (n + 1))
     outs = []
-    for path in (0, 1):
+    for path in (0, 2):
         with lib.Engine(n) as eng:
             eng.set_option("hpsi_path", path)
             eng.set_interaction(qb.interaction_matrix(qbits.positions))

@@ -22,15 +22,17 @@ for n in sizes:
         t_diag = time.time() - t0
         eng.reset_state()
         eng.evolve_schedule(np.full(3, 3.0), np.full(3, -4.0), np.full(3, 0.001))
-        for path in (0, 1):
+        for path, sb in ((2, 20), (0, 16), (0, 18), (0, 19), (0, 20), (0, 21)):
+            if sb > n:
+                continue
             eng.set_option("hpsi_path", path)
+            eng.set_option("sb_bits", sb)
             ms = eng.time_apply_h(3.0, -4.0, 12, False)[2:]
             gbs = 40.0 * (1 << n) / (np.median(ms) * 1e-3) / 1e9
-            print(json.dumps({"n": n, "path": path, "passes": eng.metrics()["hpsi_passes"], "hpsi_ms": float(np.median(ms)),
-                              "hpsi_gbs_40B": gbs, "frac_measured_peak": gbs / PEAK}))
-            if n > 26:
-                break
+            print(json.dumps({"n": n, "path": path, "sb": sb, "passes": eng.metrics()["hpsi_passes"], "hpsi_ms": round(float(np.median(ms)), 4),
+                              "hpsi_gbs_40B": round(gbs, 1), "frac_measured_peak": round(gbs / PEAK, 4)}))
         eng.set_option("hpsi_path", 0)
+        eng.set_option("sb_bits", 19)
         steps = 10
         om = np.linspace(1.0, 6.0, steps); de = np.linspace(-10, 10, steps); dt = np.full(steps, 0.001)
         ms = eng.time_schedule(om, de, dt)
