@@ -57,50 +57,64 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every 5 ms).
 
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    Same quantities as the nvidia-smi line of B200_PROFILING.md (clocks.sm, clocks.max.sm,
+    clocks_event_reasons.*), polled in-process so that sub-second regions still get samples.
+    """
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, device: int):
         self.device = device
-        self.proc = None
+        self.samples, self.reasons, self.power = [], set(), []
+        self.max_mhz = None
+        self._stop = None
+        self._thread = None
+        self._err = None
+
+    def _run(self, nv, handle):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(handle) / 1000.0)
+            except Exception as exc:  # keep timing even if NVML hiccups
+                self._err = str(exc)
+                return
+            time.sleep(0.005)
 
     def start(self):
+        import threading
+
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml as nv
+
+            nv.nvmlInit()
+            idx = int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[self.device]) \
+                if os.environ.get("CUDA_VISIBLE_DEVICES") else self.device
+            handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+        except Exception as exc:
+            self._err = str(exc)
+            return
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, args=(nv, handle), daemon=True)
+        self._thread.start()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "samples": len(self.samples), "reasons": sorted(self.reasons),
+               "power_w_max": max(self.power) if self.power else None}
+        if self._err:
+            out["error"] = self._err
+        return out
 
 
 # --------------------------------------------------------------------------------------------
@@ -115,6 +129,8 @@ def cpu_port_run(n_qubits: int, steps: int, warmup: int, budget_s: float):
     v = orc.interaction_matrix(qbits.positions)
     e = c_port.build_diagonal(v, n_qubits)
     om, de, dt = orc.flatten_schedule([(amp.values, amp.duration)], [(det.values, det.duration)])
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm is entitled to every host core
+    c_port.set_threads(os.cpu_count() or 1)
     cores = c_port.threads()
     psi = np.zeros(1 << n_qubits, dtype=np.complex128)
     psi[0] = 1.0
@@ -244,12 +260,19 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     met = eng.metrics()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernel": f"H psi = {met['hpsi_passes']} launches of hpsi_tile_kernel (passes), timed as a group",
+                "kernel": f"H psi = {met['hpsi_passes']} launches of hpsi_ws_kernel (fused super-block launch + plain pass), timed as a group",
                 "algorithmic_bytes_per_launch_group": BYTES_PER_AMP * amps_total / world,
                 "planned_hbm_bytes_per_amp": met["hpsi_bytes_per_amp"],
                 "hpsi_ms": t_hpsi * 1e3,
                 "in_sweep": {"achieved": value / world, "frac": value / world / peak,
                              "note": "fused Taylor step: same 40 B/amp currency, region time / number of H psi"}}
+
+    if world > 1:
+        inbound = 16.0 * (1 << (n - p)) * p  # partner shards read over NVLink per H psi per GPU
+        roofline["nvlink"] = {"bound": "nvlink", "achieved": inbound / t_hpsi / 1e9, "peak": 770.0, "unit": "GB/s",
+                              "frac": inbound / t_hpsi / 1e9 / 770.0, "peak_source": "measured peer copy per direction "
+                              "(B200_PROFILING.md); nominal 900", "bytes_per_hpsi_per_gpu": inbound,
+                              "note": "partner amplitudes are read inside pass 0; time = whole H psi"}
 
     # ---- e2e: the plugin call with host buffers -------------------------------------------
     eng.close()

@@ -65,8 +65,16 @@ int qsb_destroy(qsb_ctx* ctx);
 int qsb_local_dim(const qsb_ctx* ctx, uint64_t* dim);   /* 2^(N-p) amplitudes in this shard */
 /* options: "tol" (Taylor term tolerance, default 1e-14), "theta_max" (sub-step bound on
  * |H| dt, default 3), "max_terms" (default 64), "fixed_terms" (0 = norm-terminated;
- * 4 = classical RK4), "hpsi_path" (0 auto, 1 force the untiled kernel) */
+ * 4 = classical RK4), "hpsi_path" (0 auto = warp-specialised super-block kernel, 1 = untiled
+ * one-thread-per-amplitude kernel, 2 = one launch per tile-bit group), "sb_bits" (log2 of the
+ * L2-resident super-block, 13..21, default 19) */
 int qsb_set_option(qsb_ctx* ctx, const char* key, double value);
+
+/* page-locked host memory for state-sized transfers (qsb_get_state / qsb_set_state run at PCIe
+ * speed into such a buffer; into pageable memory the driver stages the copy).  Free with
+ * qsb_host_free.  The reference keeps its state in ordinary numpy memory (qse/calc/qutip.py:49). */
+int qsb_host_alloc(uint64_t bytes, void** out);
+int qsb_host_free(void* ptr);
 
 /* ---- Hamiltonian ------------------------------------------------------------------ */
 /* replaces: Qutip._build_hamiltonian_operators -> ham_int (qse/calc/qutip.py:60-64) and

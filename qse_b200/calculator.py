@@ -366,7 +366,7 @@ class B200(_Base):
         if self._statevector is None:
             if self._engine is None:
                 return None
-            local = self._engine.get_state()
+            local = self._engine.get_state(pinned=True)  # page-locked: the copy runs at PCIe speed
             if self._engine.nranks > 1:
                 from . import distributed as qdist
 

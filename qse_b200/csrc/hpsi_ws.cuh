@@ -72,7 +72,9 @@ QSB_DEV u64 ws_tile_base(int lb, int hb, int hb0, u64 tau) {
 // FIRST = contiguous tile (bits 0..11 + diagonal + peers); otherwise strided rows (bits >= lb)
 // Global operands (E_int or partial y, and the Taylor accumulator) are requested up front with
 // loads the compiler may not sink, so their latency hides behind the shared-memory flip phase.
-template <bool FIRST>
+// PEER (FIRST only): sharded-qubit partners are read over NVLink; x is then re-read from the tile
+// at the end instead of being kept live, to make room for the partner amplitudes in flight.
+template <bool FIRST, bool PEER>
 QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 base, bool last, int t, double& nrm) {
     const int lb = FIRST ? kTileBits : p.lb;
     const int hb0 = FIRST ? kTileBits : p.hb0;
@@ -82,11 +84,15 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
 #define QSB_GADDR(j) (base | ((((u64)(t + (j)*512)) >> lb) << hb0) | (((u64)(t + (j)*512)) & low_mask))
 
     double e[kPerThread];
-    double2 yv[kPerThread];
+    double2 yv[kPerThread];  // non-FIRST: partial y; FIRST+PEER: first partner's amplitudes; FIRST: x
 #pragma unroll
     for (int j = 0; j < kPerThread; ++j) {
-        if (FIRST) e[j] = ldnc1(p.eint + QSB_GADDR(j));
-        else yv[j] = ldcg2(p.y + QSB_GADDR(j));
+        if (FIRST) {
+            e[j] = ldnc1(p.eint + QSB_GADDR(j));
+            if (PEER) yv[j] = ldg2_volatile(p.peer[0] + QSB_GADDR(j));  // over NVLink
+        } else {
+            yv[j] = ldcg2(p.y + QSB_GADDR(j));
+        }
     }
     double2 sum[kPerThread];
     {
@@ -101,9 +107,7 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
                 if (kSmemBits + b >= act_lo) cacc(a, xv[j ^ (1 << b)]);
             sum[j] = a;
         }
-        if (FIRST) {
-            // fold the diagonal term in now so that x need not stay live: sum <- (d/half_omega)... no:
-            // keep exactness: y = d*x + h*sum, so stash d*x in e[] / yv[] instead.
+        if (FIRST && !PEER) {
 #pragma unroll
             for (int j = 0; j < kPerThread; ++j) yv[j] = xv[j];
         }
@@ -120,10 +124,16 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
 #pragma unroll
             for (int j = 0; j < kPerThread; ++j) cacc(sum[j], ts[tb + j * 512]);
         }
-        for (int q = 0; q < p.n_peer; ++q) {
+        if (PEER) {
+#pragma unroll
+            for (int j = 0; j < kPerThread; ++j) cacc(sum[j], yv[j]);
+        }
+        for (int q = 1; PEER && q < p.n_peer; ++q) {
             const double2* __restrict__ px = p.peer[q];
 #pragma unroll
-            for (int j = 0; j < kPerThread; ++j) cacc(sum[j], px[QSB_GADDR(j)]);
+            for (int j = 0; j < kPerThread; ++j) yv[j] = ldg2_volatile(px + QSB_GADDR(j));
+#pragma unroll
+            for (int j = 0; j < kPerThread; ++j) cacc(sum[j], yv[j]);
         }
     } else {
         for (int b = act_lo; b < kSmemBits; ++b) {
@@ -138,7 +148,8 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
         double2 v;
         if (FIRST) {
             const double d = e[j] - p.delta * (double)(__popcll(g) + p.pop_rank);
-            v = make_double2(d * yv[j].x + p.half_omega * sum[j].x, d * yv[j].y + p.half_omega * sum[j].y);
+            const double2 xj = PEER ? ts[t + j * 512] : yv[j];
+            v = make_double2(d * xj.x + p.half_omega * sum[j].x, d * xj.y + p.half_omega * sum[j].y);
         } else {
             v = make_double2(yv[j].x + p.half_omega * sum[j].x, yv[j].y + p.half_omega * sum[j].y);
         }
@@ -252,7 +263,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p) 
             const int sb = desc[s].sb;
             const double2* ts = tiles + (size_t)s * kTile;
             if (type == kItemFirst) {
-                ws_process<true>(p, ts, base, false, t, nrm);
+                if (p.n_peer > 0) ws_process<true, true>(p, ts, base, false, t, nrm);
+                else ws_process<true, false>(p, ts, base, false, t, nrm);
                 // publish this tile of partial y: warp barrier -> cta-scope release on the shared
                 // counter; the 16th warp to finish issues ONE gpu-scope fence (cumulative over the
                 // writes it observed through the counter) and bumps the super-block counter.
@@ -267,7 +279,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p) 
                     }
                 }
             } else {
-                ws_process<false>(p, ts, base, p.last != 0, t, nrm);
+                ws_process<false, false>(p, ts, base, p.last != 0, t, nrm);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);

@@ -736,6 +736,21 @@ int qsb_destroy(qsb_ctx* c) {
     return QSB_OK;
 }
 
+int qsb_host_alloc(uint64_t bytes, void** out) {
+    qsb_ctx* c = nullptr;
+    if (!out || bytes == 0) return fail(c, QSB_ERR_INVALID, "bad argument");
+    *out = nullptr;
+    CU(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    return QSB_OK;
+}
+
+int qsb_host_free(void* ptr) {
+    qsb_ctx* c = nullptr;
+    if (!ptr) return QSB_OK;
+    CU(cudaFreeHost(ptr));
+    return QSB_OK;
+}
+
 int qsb_local_dim(const qsb_ctx* ctx, uint64_t* dim) {
     if (!ctx || !dim) return fail(nullptr, QSB_ERR_INVALID, "NULL argument");
     *dim = ctx->dim;

@@ -56,6 +56,8 @@ SIGNATURES = {
     "qsb_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_ctx_p)]),
     "qsb_create_sharded": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(_ctx_p)]),
     "qsb_destroy": (C.c_int, [_ctx_p]),
+    "qsb_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
+    "qsb_host_free": (C.c_int, [C.c_void_p]),
     "qsb_local_dim": (C.c_int, [_ctx_p, _c_u64_p]),
     "qsb_set_option": (C.c_int, [_ctx_p, C.c_char_p, C.c_double]),
     "qsb_set_interaction": (C.c_int, [_ctx_p, _c_double_p]),
@@ -144,6 +146,22 @@ def nccl_unique_id() -> bytes:
     return buf.raw
 
 
+def pinned_empty(n: int, dtype=np.complex128) -> np.ndarray:
+    """1-D array of ``n`` elements in page-locked host memory (freed when the array is collected)."""
+    import weakref
+
+    lib = load()
+    nbytes = int(n) * np.dtype(dtype).itemsize
+    ptr = C.c_void_p()
+    rc = lib.qsb_host_alloc(nbytes, C.byref(ptr))
+    if rc != 0:
+        raise QsbError(rc, lib.qsb_last_error(None).decode())
+    buf = (C.c_char * nbytes).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+    weakref.finalize(buf, lib.qsb_host_free, ptr)
+    return arr
+
+
 def _dp(a: np.ndarray):
     return a.ctypes.data_as(_c_double_p)
 
@@ -220,9 +238,10 @@ class Engine:
             raise ValueError(f"state shard must hold {self.local_dim} amplitudes")
         self._check(self._lib.qsb_set_state(self._ctx, psi.view(np.float64).ctypes.data_as(_c_double_p)))
 
-    def get_state(self, out: np.ndarray | None = None) -> np.ndarray:
+    def get_state(self, out: np.ndarray | None = None, pinned: bool = False) -> np.ndarray:
         if out is None:
-            out = np.empty(self.local_dim, dtype=np.complex128)
+            big = pinned and self.local_dim >= (1 << 18)
+            out = pinned_empty(self.local_dim) if big else np.empty(self.local_dim, dtype=np.complex128)
         self._check(self._lib.qsb_get_state(self._ctx, out.view(np.float64).ctypes.data_as(_c_double_p)))
         return out
 
