@@ -40,6 +40,16 @@ def is_stale() -> bool:
     return any(os.path.getmtime(p) > built for p in SOURCES + HEADERS)
 
 
+def build_variant(out: str, defines: list[str]) -> str:
+    """Developer A/B builds: same sources with extra -D macros into another .so (see tools/)."""
+    cmd = [find_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out, *SOURCES, "-ldl"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("nvcc failed")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile libqsb.so if missing or older than its sources; returns the library path."""
     if not force and not is_stale():

@@ -338,6 +338,7 @@ class B200(_Base):
         t2 = time.time()
         after = eng.metrics()
         self._statevector = None
+        self.results = None  # drop our own references to the previous state buffer
         result = {}
         if self.return_state:
             result["state"] = self.statevector.reshape(-1, 1)
@@ -366,13 +367,29 @@ class B200(_Base):
         if self._statevector is None:
             if self._engine is None:
                 return None
-            local = self._engine.get_state(pinned=True)  # page-locked: the copy runs at PCIe speed
+            local = self._engine.get_state(out=self._state_buffer(self._engine.local_dim))
             if self._engine.nranks > 1:
                 from . import distributed as qdist
 
                 local = qdist.gather_shards(local)
             self._statevector = local
         return self._statevector
+
+    def _state_buffer(self, n: int):
+        """Page-locked host buffer for the state read-back (PCIe speed instead of a staged copy).
+
+        Locking memory is slow (~0.3 ms/MiB), so the buffer is kept and reused by the next
+        ``calculate()`` — but only if nobody else still references it (a result the caller kept
+        is never overwritten; a new buffer is locked instead)."""
+        import sys
+
+        if n < (1 << 18):
+            return None
+        buf = getattr(self, "_pinned", None)
+        if buf is None or buf.size != n or sys.getrefcount(buf) > 2:
+            buf = lib.pinned_empty(n)
+            self._pinned = buf
+        return buf
 
     @statevector.setter
     def statevector(self, value):

@@ -19,18 +19,39 @@
 // HBM traffic per amplitude: 40 B for the fused launch + 48 B per plain launch (25 qubits: 88 B
 // instead of 136 B with one launch per tile-bit group).
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 #include "hpsi.cuh"
 
 namespace qsb {
 
-constexpr int kWsStages = 3;
 constexpr int kConsumerWarps = 16;
 // warps 0..15 consume, warp 16 produces, warps 17..19 only pad the producer to a full warpgroup:
 // registers are allocated per warpgroup, and setmaxnreg moves the producer group's share
-// (96 -> 24 per thread) to the consumers (96 -> 112).
+// (96 -> 32 per thread) to the consumers (96 -> 112).
 constexpr int kWsThreads = (kConsumerWarps + 4) * 32;  // 640
-constexpr size_t kWsSmemBytes = (size_t)kWsStages * kTile * sizeof(double2);
+constexpr size_t kWsSmemBytes = 192 * 1024;            // the tile ring
+
+// Tile geometry.  A tile holds 2^TB amplitudes; a consumer thread owns 8 of them, so a tile is
+// processed by a GROUP of 2^(TB-3) threads and the 16 consumer warps form 16*32 / 2^(TB-3)
+// independent groups (group g takes work items g, g + kGroups, ...).  TB = 12: one group, 3 stages
+// of 64 KiB.  TB = 11: two groups, 6 stages of 32 KiB -- same total shared-memory work per H psi
+// (19 LDS.128 per amplitude at 25 qubits either way) but two tiles in flight per group, which is
+// what hides the 3-5 us it takes the TMA engine to land a tile, and two groups that drift out of
+// phase so that the flip phase of one overlaps the global loads/stores of the other.
+template <int TB>
+struct WsCfg {
+    static constexpr int kTileBitsW = TB;
+    static constexpr int kTileW = 1 << TB;
+    static constexpr int kGroupThreads = kTileW / kPerThread;
+    static constexpr int kGroupWarps = kGroupThreads / 32;
+    static constexpr int kGroups = kConsumerWarps / kGroupWarps;
+    static constexpr int kRegLo = TB - kRegBits;  // tile bits [kRegLo, TB) are register-only flips
+    static constexpr int kStages = (int)(kWsSmemBytes / (kTileW * sizeof(double2)));
+    static_assert(kGroups >= 1 && kStages >= 2 && kStages <= 12, "tile size");
+};
+constexpr int kMaxStages = 12;
 
 enum { kItemFirst = 0, kItemInner = 1, kItemPlain = 2, kItemDone = 3 };
 
@@ -52,14 +73,16 @@ struct HpsiWs {
     double2 scale;
     int nl;
     int pop_rank;
-    int fused;       // 1: fused A+B launch over super-blocks; 0: plain launch
+    int fused;       // 1: fused FIRST+INNER launch over super-blocks; 0: plain launch
     int sbits;       // fused: log2 of the super-block
-    int lb, hb, hb0; // geometry of the strided tiles (inner sub-pass or plain pass)
+    int lb, hb, hb0; // geometry of the strided tiles (inner sub-pass or plain pass): lb + hb = TB
     int last;        // the strided tiles of this launch finish H psi (apply scale / acc / norm)
+    int lag;         // fused: lead of the FIRST tiles over the INNER tiles, in super-blocks
     unsigned int* ticket;
-    unsigned long long* done;   // per super-block: A tiles completed (cumulative over launches)
+    unsigned long long* done;   // per super-block: FIRST tiles completed (cumulative over launches)
     unsigned long long done_target;
-    u64 n_tiles;     // tiles per sub-pass (= dim / 4096)
+    u64 n_tiles;     // tiles per sub-pass (= dim >> TB)
+    int use_tmap;    // strided tiles are fetched with ONE 2-D tensor-map TMA per <= 256 rows
 };
 
 QSB_DEV u64 ws_tile_base(int lb, int hb, int hb0, u64 tau) {
@@ -69,19 +92,24 @@ QSB_DEV u64 ws_tile_base(int lb, int hb, int hb0, u64 tau) {
     return (outer << (hb0 + hb)) | (mid << lb);
 }
 
-// FIRST = contiguous tile (bits 0..11 + diagonal + peers); otherwise strided rows (bits >= lb)
-// Global operands (E_int or partial y, and the Taylor accumulator) are requested up front with
-// loads the compiler may not sink, so their latency hides behind the shared-memory flip phase.
+// FIRST = contiguous tile (bits 0..TB-1 + diagonal + peers); otherwise strided rows (bits >= lb).
+// A thread owns tile indices idx = t + j * kGroupThreads (j = 0..7): tile bits [TB-3, TB) are
+// register-only flips, every other active tile bit is a conflict-free LDS.128 at an XOR-permuted
+// address.  Global operands (E_int or partial y, the Taylor accumulator, the first NVLink partner)
+// are requested up front with loads the compiler may not sink, so their latency hides behind the
+// shared-memory flip phase.
 // PEER (FIRST only): sharded-qubit partners are read over NVLink; x is then re-read from the tile
 // at the end instead of being kept live, to make room for the partner amplitudes in flight.
-template <bool FIRST, bool PEER>
+template <int TB, bool FIRST, bool PEER>
 QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 base, bool last, int t, double& nrm) {
-    const int lb = FIRST ? kTileBits : p.lb;
-    const int hb0 = FIRST ? kTileBits : p.hb0;
+    using C = WsCfg<TB>;
+    const int lb = FIRST ? TB : p.lb;
+    const int hb0 = FIRST ? TB : p.hb0;
     const u64 low_mask = (1ull << lb) - 1ull;
     const int act_lo = FIRST ? 0 : lb;
     const bool with_acc = last && p.acc != nullptr;
-#define QSB_GADDR(j) (base | ((((u64)(t + (j)*512)) >> lb) << hb0) | (((u64)(t + (j)*512)) & low_mask))
+#define QSB_IDX(j) (t + (j)*C::kGroupThreads)
+#define QSB_GADDR(j) (base | ((((u64)QSB_IDX(j)) >> lb) << hb0) | (((u64)QSB_IDX(j)) & low_mask))
 
     double e[kPerThread];
     double2 yv[kPerThread];  // non-FIRST: partial y; FIRST+PEER: first partner's amplitudes; FIRST: x
@@ -98,13 +126,13 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
     {
         double2 xv[kPerThread];
 #pragma unroll
-        for (int j = 0; j < kPerThread; ++j) xv[j] = ts[t + j * 512];
+        for (int j = 0; j < kPerThread; ++j) xv[j] = ts[QSB_IDX(j)];
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) {
             double2 a = make_double2(0.0, 0.0);
 #pragma unroll
             for (int b = 0; b < kRegBits; ++b)
-                if (kSmemBits + b >= act_lo) cacc(a, xv[j ^ (1 << b)]);
+                if (C::kRegLo + b >= act_lo) cacc(a, xv[j ^ (1 << b)]);
             sum[j] = a;
         }
         if (FIRST && !PEER) {
@@ -119,10 +147,10 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
     }
     if (FIRST) {
 #pragma unroll
-        for (int b = 0; b < kSmemBits; ++b) {
+        for (int b = 0; b < C::kRegLo; ++b) {
             const int tb = t ^ (1 << b);
 #pragma unroll
-            for (int j = 0; j < kPerThread; ++j) cacc(sum[j], ts[tb + j * 512]);
+            for (int j = 0; j < kPerThread; ++j) cacc(sum[j], ts[tb + j * C::kGroupThreads]);
         }
         if (PEER) {
 #pragma unroll
@@ -136,10 +164,10 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
             for (int j = 0; j < kPerThread; ++j) cacc(sum[j], yv[j]);
         }
     } else {
-        for (int b = act_lo; b < kSmemBits; ++b) {
+        for (int b = act_lo; b < C::kRegLo; ++b) {
             const int tb = t ^ (1 << b);
 #pragma unroll
-            for (int j = 0; j < kPerThread; ++j) cacc(sum[j], ts[tb + j * 512]);
+            for (int j = 0; j < kPerThread; ++j) cacc(sum[j], ts[tb + j * C::kGroupThreads]);
         }
     }
 #pragma unroll
@@ -148,7 +176,7 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
         double2 v;
         if (FIRST) {
             const double d = e[j] - p.delta * (double)(__popcll(g) + p.pop_rank);
-            const double2 xj = PEER ? ts[t + j * 512] : yv[j];
+            const double2 xj = PEER ? ts[QSB_IDX(j)] : yv[j];
             v = make_double2(d * xj.x + p.half_omega * sum[j].x, d * xj.y + p.half_omega * sum[j].y);
         } else {
             v = make_double2(yv[j].x + p.half_omega * sum[j].x, yv[j].y + p.half_omega * sum[j].y);
@@ -161,15 +189,18 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
         p.y[g] = v;
     }
 #undef QSB_GADDR
+#undef QSB_IDX
 }
 
-__global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p) {
+template <int TB>
+__global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, const __grid_constant__ CUtensorMap tmap) {
+    using C = WsCfg<TB>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2* tiles = reinterpret_cast<double2*>(smem_raw);
-    __shared__ __align__(8) uint64_t full_bar[kWsStages];
-    __shared__ __align__(8) uint64_t empty_bar[kWsStages];
-    __shared__ WsItem desc[kWsStages];
-    __shared__ int warps_done[kWsStages];
+    __shared__ __align__(8) uint64_t full_bar[C::kStages];
+    __shared__ __align__(8) uint64_t empty_bar[C::kStages];
+    __shared__ WsItem desc[C::kStages];
+    __shared__ int warps_done[C::kStages];
     __shared__ double red[32];
 
     const int t = threadIdx.x;
@@ -177,9 +208,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p) 
 
     if (t == 0) {
 #pragma unroll
-        for (int s = 0; s < kWsStages; ++s) {
+        for (int s = 0; s < C::kStages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kConsumerWarps);
+            mbar_init(&empty_bar[s], C::kGroupWarps);
             warps_done[s] = 0;
         }
         mbar_fence_init();
@@ -191,95 +222,129 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p) 
         // ================= producer warpgroup (only its first warp works) =================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         if (warp == kConsumerWarps) {
-        const u64 n_a = p.fused ? (1ull << (p.sbits - kTileBits)) : 0;  // tiles per super-block sub-pass
-        const u64 n_sb = p.fused ? (p.n_tiles / n_a) : 0;
-        const u64 total = p.fused ? 2ull * p.n_tiles : p.n_tiles;
-        for (u64 it = 0;; ++it) {
-            const int s = (int)(it % kWsStages);
-            const u64 use = it / kWsStages;
-            if (use > 0) mbar_wait(&empty_bar[s], (uint32_t)((use - 1) & 1ull));
-            unsigned int ticket = 0;
-            if (lane == 0) ticket = atomicAdd(p.ticket, 1u);
-            ticket = __shfl_sync(0xffffffffu, ticket, 0);
-            if ((u64)ticket >= total) {
+            // Static schedule from ONE global ticket counter.  Tickets enumerate phases of n_a tiles:
+            //   A(0) .. A(L-1),  then  A(s), B(s-L)  for s = L .. n_sb-1,  then  B(n_sb-L) .. B(n_sb-1)
+            // (A = FIRST tiles of a super-block, B = its INNER tiles, L = p.lag super-blocks of lead).
+            // B(s) is handed out L phases after A(s), so its dependency is normally already satisfied
+            // when the ticket is taken; the producer still checks done[s] and waits if it is not.  It
+            // only ever waits for tickets taken earlier by running CTAs: no deadlock whatever the
+            // residency.  (A dynamic two-queue scheduler was measured slower: its extra L2 round
+            // trips per item put the producer on the critical path.)
+            const u64 n_a = p.fused ? (1ull << (p.sbits - TB)) : 1;  // tiles per super-block
+            const u64 n_sb = p.fused ? (p.n_tiles / n_a) : 0;
+            const u64 lag = p.fused ? ((u64)p.lag < n_sb ? (u64)(p.lag < 1 ? 1 : p.lag) : n_sb) : 0;
+            const u64 total = p.fused ? 2ull * p.n_tiles : p.n_tiles;
+            int n_done = 0;
+            for (u64 it = 0;; ++it) {
+                const int s = (int)(it % C::kStages);
+                const u64 use = it / C::kStages;
+                if (use > 0) mbar_wait(&empty_bar[s], (uint32_t)((use - 1) & 1ull));
+                int type = kItemDone;
+                u64 tau = 0;
+                if (lane == 0 && n_done == 0) {
+                    const u64 ticket = atomicAdd(p.ticket, 1u);
+                    if (ticket < total) {
+                        if (!p.fused) {
+                            type = kItemPlain;
+                            tau = ticket;
+                        } else {
+                            const u64 ph = ticket / n_a, wi = ticket % n_a;
+                            u64 sb;
+                            if (ph < lag) { type = kItemFirst; sb = ph; }
+                            else if (ph < 2 * n_sb - lag) {
+                                const u64 q = ph - lag;
+                                if (q & 1ull) { type = kItemInner; sb = q >> 1; }
+                                else { type = kItemFirst; sb = lag + (q >> 1); }
+                            } else { type = kItemInner; sb = n_sb - lag + (ph - (2 * n_sb - lag)); }
+                            tau = sb * n_a + wi;
+                        }
+                    }
+                }
+                type = __shfl_sync(0xffffffffu, type, 0);
+                tau = __shfl_sync(0xffffffffu, tau, 0);
+                if (type == kItemDone) {
+                    // out of work: one sentinel per consumer group (consecutive items go to distinct groups)
+                    if (lane == 0) {
+                        desc[s].type = kItemDone;
+                        mbar_arrive(&full_bar[s]);
+                    }
+                    if (++n_done == C::kGroups) break;
+                    continue;
+                }
+                const int sb = (int)(tau / n_a);
+                double2* stage = tiles + (size_t)s * C::kTileW;
+                u64 base;
+                if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(C::kTileW * sizeof(double2)));
+                __syncwarp();
+                if (type == kItemFirst) {
+                    base = tau << TB;
+                    constexpr int kCopies = 4;  // per-copy overhead of the TMA engine favours few large copies
+                    constexpr int chunk = C::kTileW / kCopies;
+                    if (lane < kCopies)
+                        bulk_g2s(stage + lane * chunk, p.x + base + (u64)lane * chunk, chunk * sizeof(double2), &full_bar[s]);
+                } else {
+                    base = ws_tile_base(p.lb, p.hb, p.hb0, tau);
+                    const int rows = 1 << p.hb;
+                    if (p.use_tmap) {
+                        // x viewed as [rows of 2^hb0 amplitudes][2 * 2^hb0 doubles]: the tile is the box
+                        // {2 * 2^lb doubles} x {2^hb rows} at (2 * (mid << lb), outer << hb)
+                        const int mid_bits = p.hb0 - p.lb;
+                        const int c0 = (int)((tau & ((1ull << mid_bits) - 1ull)) << (p.lb + 1));
+                        const int c1 = (int)((tau >> mid_bits) << p.hb);
+                        if (lane < ((rows + 255) >> 8))
+                            tma_load_2d(stage + ((size_t)(lane * 256) << p.lb), &tmap, c0, c1 + lane * 256, &full_bar[s]);
+                    } else {
+                        const uint32_t row_bytes = (uint32_t)(sizeof(double2) << p.lb);
+                        for (int r = lane; r < rows; r += 32)
+                            bulk_g2s(stage + ((size_t)r << p.lb), p.x + base + ((u64)r << p.hb0), row_bytes, &full_bar[s]);
+                    }
+                }
                 if (lane == 0) {
-                    desc[s].type = kItemDone;
-                    mbar_arrive(&full_bar[s]);
+                    if (type == kItemInner) {
+                        // the partial y of this super-block must be complete (all its FIRST tiles stored)
+                        while (ld_volatile_u64(p.done + sb) < p.done_target) __nanosleep(32);
+                        __threadfence();  // acquire side of the done[] handshake
+                    }
+                    desc[s].base = base;
+                    desc[s].type = type;
+                    desc[s].sb = sb;
+                    mbar_arrive(&full_bar[s]);  // release: descriptor (and the INNER dependency) visible to consumers
                 }
-                break;
+                __syncwarp();
             }
-            int type, sb = 0;
-            u64 tau;
-            if (p.fused) {
-                const u64 ph = ticket / n_a, w = ticket % n_a;
-                if (ph == 0) { type = kItemFirst; sb = 0; }
-                else if (ph == 2 * n_sb - 1) { type = kItemInner; sb = (int)(n_sb - 1); }
-                else if (ph & 1ull) { type = kItemFirst; sb = (int)((ph + 1) / 2); }
-                else { type = kItemInner; sb = (int)(ph / 2 - 1); }
-                tau = (u64)sb * n_a + w;
-            } else {
-                type = kItemPlain;
-                tau = ticket;
-            }
-            double2* stage = tiles + (size_t)s * kTile;
-            u64 base;
-            if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(kTile * sizeof(double2)));
-            __syncwarp();
-            if (type == kItemFirst) {
-                base = tau << kTileBits;
-                constexpr int chunk = kTile / 32;
-                bulk_g2s(stage + lane * chunk, p.x + base + (u64)lane * chunk, chunk * sizeof(double2), &full_bar[s]);
-            } else {
-                base = ws_tile_base(p.lb, p.hb, p.hb0, tau);
-                const int rows = 1 << p.hb;
-                const uint32_t row_bytes = (uint32_t)(sizeof(double2) << p.lb);
-                for (int r = lane; r < rows; r += 32)
-                    bulk_g2s(stage + ((size_t)r << p.lb), p.x + base + ((u64)r << p.hb0), row_bytes, &full_bar[s]);
-            }
-            if (lane == 0) {
-                if (type == kItemInner) {
-                    // the partial y of this super-block must be complete (all its A tiles stored)
-                    while (ld_acquire_u64(p.done + sb) < p.done_target) __nanosleep(32);
-                    __threadfence();
-                }
-                desc[s].base = base;
-                desc[s].type = type;
-                desc[s].sb = sb;
-                mbar_arrive(&full_bar[s]);  // release: descriptor + dependency visible to consumers
-            }
-            __syncwarp();
-        }
         }
     } else {
         // ================= consumer warps =================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-        for (u64 it = 0;; ++it) {
-            const int s = (int)(it % kWsStages);
-            const u64 use = it / kWsStages;
+        const int group = warp / C::kGroupWarps;
+        const int tg = t - group * C::kGroupThreads;  // thread index within the group
+        for (u64 it = (u64)group;; it += C::kGroups) {
+            const int s = (int)(it % C::kStages);
+            const u64 use = it / C::kStages;
             mbar_wait(&full_bar[s], (uint32_t)(use & 1ull));
             const int type = desc[s].type;
             if (type == kItemDone) break;
             const u64 base = desc[s].base;
             const int sb = desc[s].sb;
-            const double2* ts = tiles + (size_t)s * kTile;
+            const double2* ts = tiles + (size_t)s * C::kTileW;
             if (type == kItemFirst) {
-                if (p.n_peer > 0) ws_process<true, true>(p, ts, base, false, t, nrm);
-                else ws_process<true, false>(p, ts, base, false, t, nrm);
+                if (p.n_peer > 0) ws_process<TB, true, true>(p, ts, base, false, tg, nrm);
+                else ws_process<TB, true, false>(p, ts, base, false, tg, nrm);
                 // publish this tile of partial y: warp barrier -> cta-scope release on the shared
-                // counter; the 16th warp to finish issues ONE gpu-scope fence (cumulative over the
-                // writes it observed through the counter) and bumps the super-block counter.
+                // counter; the last warp of the group to finish issues ONE gpu-scope fence (cumulative
+                // over the writes it observed through the counter) and bumps the super-block counter.
                 __syncwarp();
                 if (lane == 0) {
                     __threadfence_block();
                     const int c = atomicAdd(&warps_done[s], 1);
-                    if (c == kConsumerWarps - 1) {
+                    if (c == C::kGroupWarps - 1) {
                         warps_done[s] = 0;
                         __threadfence();
                         atomicAdd(p.done + sb, 1ull);
                     }
                 }
             } else {
-                ws_process<false, false>(p, ts, base, p.last != 0, t, nrm);
+                ws_process<TB, false, false>(p, ts, base, p.last != 0, tg, nrm);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);

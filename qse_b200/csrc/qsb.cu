@@ -46,11 +46,20 @@ struct qsb_ctx {
     HpsiPlan plan;
     // warp-specialised super-block path (hpsi_ws.cuh)
     int path = 0;       // 0 auto (ws when N_local >= 13), 1 untiled, 2 one launch per tile-bit group
-    int sb_bits = 19;   // log2 of the L2-resident super-block (2 x 20 MiB in flight: measured best on B200)
+    int sb_lag = 3;     // lead of the FIRST tiles over the INNER tiles of the fused launch, in super-blocks
+    int ws_tile_bits = 12;  // 12 (64 KiB tiles, 3 stages; measured best) or 11 (32 KiB tiles, 6 stages, two groups); 0 = fewest launches
+    int sb_bits = 18;   // log2 of the L2-resident super-block (10 MiB each; 18 / lead 3 measured best on B200)
     unsigned int* tickets = nullptr;        // one work counter per launch of an H psi
     unsigned long long* sb_done = nullptr;  // per super-block completion counters (cumulative)
     unsigned long long ws_epoch = 0;
-    int ws_sbits_active = -1;  // super-block size the completion counters were accumulated with
+    int ws_sbits_active = -1;
+    int use_tmap = 1;  // option "tensor_map": 2-D tensor-map TMA for strided tiles (0 = one bulk copy per row)
+    struct TmapEntry {
+        const void* ptr;
+        int lb, hb, hb0;
+        CUtensorMap map;
+    };
+    std::vector<TmapEntry> tmaps;  // super-block size the completion counters were accumulated with
     // options
     double tol = 1e-14, theta_max = 3.0;
     int max_terms = 64, fixed_terms = 0, force_flat = 0;
@@ -146,38 +155,82 @@ static const double2* peer_of(qsb_ctx* c, const double2* x, int partner) {
 }
 
 struct WsPlan {
+    int tb;     // tile bits (11 or 12)
     int sbits;
     PassGeom inner;
     int n_plain;
-    PassGeom plain[6];
+    PassGeom plain[8];
     double bytes_per_amp;
 };
-static WsPlan make_ws_plan(int nl, int sb_bits) {
+static WsPlan make_ws_plan_tb(int nl, int sb_bits, int tb) {
     WsPlan w{};
-    w.sbits = std::min(nl, std::min(sb_bits, kTileBits + 9));
-    const int hb = w.sbits - kTileBits;
-    w.inner = PassGeom{kTileBits - hb, hb, kTileBits};
+    w.tb = tb;
+    const int max_hb = tb - 3;  // keep >= 128-byte rows
+    w.sbits = std::max(tb + 1, std::min(nl, std::min(sb_bits, tb + max_hb)));
+    if (w.sbits > nl) w.sbits = nl;
+    const int hb = w.sbits - tb;
+    w.inner = PassGeom{tb - hb, hb, tb};
     w.bytes_per_amp = 40.0;
     int rem = nl - w.sbits;
-    const int max_hb = kTileBits - 3;
     const int extra = (rem + max_hb - 1) / max_hb;
     int pos = w.sbits;
     for (int i = 0; i < extra; ++i) {
         const int h = (rem + (extra - i) - 1) / (extra - i);
-        w.plain[w.n_plain++] = PassGeom{kTileBits - h, h, pos};
+        w.plain[w.n_plain++] = PassGeom{tb - h, h, pos};
         w.bytes_per_amp += 48.0;
         pos += h;
         rem -= h;
     }
     return w;
 }
+static WsPlan make_ws_plan(int nl, int sb_bits, int tile_bits) {
+    if (tile_bits == 11 || tile_bits == 12) return make_ws_plan_tb(nl, sb_bits, tile_bits);
+    const WsPlan a = make_ws_plan_tb(nl, sb_bits, 11), b = make_ws_plan_tb(nl, sb_bits, 12);
+    return (a.n_plain <= b.n_plain) ? a : b;
+}
+
+// 2-D tensor map over a state-sized vector for strided tiles {2^lb amplitudes} x {2^hb rows, stride 2^hb0}
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int get_tmap(qsb_ctx* c, const double2* x, int lb, int hb, int hb0, const CUtensorMap** out) {
+    for (auto& e : c->tmaps)
+        if (e.ptr == x && e.lb == lb && e.hb == hb && e.hb0 == hb0) {
+            *out = &e.map;
+            return QSB_OK;
+        }
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(c, QSB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+        encode = (EncodeTiledFn)fn;
+    }
+    qsb_ctx::TmapEntry e;
+    e.ptr = x;
+    e.lb = lb;
+    e.hb = hb;
+    e.hb0 = hb0;
+    const cuuint64_t gdim[2] = {2ull << hb0, 1ull << (c->nl - hb0)};
+    const cuuint64_t gstride[1] = {16ull << hb0};
+    const cuuint32_t box[2] = {2u << lb, (cuuint32_t)std::min(1 << hb, 256)};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult r = encode(&e.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)x, gdim, gstride, box, estride,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, QSB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for lb=%d hb=%d hb0=%d", (int)r, lb, hb, hb0);
+    c->tmaps.push_back(e);
+    *out = &c->tmaps.back().map;
+    return QSB_OK;
+}
 
 // warp-specialised path: one fused launch over L2-resident super-blocks + plain launches for the
 // index bits above the super-block (hpsi_ws.cuh)
 static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, double omega, double delta, bool fuse,
                           double2 scale, double2* acc, double* norm_slot, const double2* const* peers) {
-    const WsPlan w = make_ws_plan(c->nl, c->sb_bits);
-    const u64 n_tiles = c->dim >> kTileBits;
+    const WsPlan w = make_ws_plan(c->nl, c->sb_bits, c->ws_tile_bits);
+    const u64 n_tiles = c->dim >> w.tb;
     const int grid = (int)std::min<u64>(n_tiles, (u64)c->n_sm);
     CU(cudaMemsetAsync(c->tickets, 0, 16 * sizeof(unsigned int), c->stream));
     HpsiWs a{};
@@ -202,20 +255,28 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, double omega
         a.hb = g.hb;
         a.hb0 = g.hb0;
         a.last = last ? 1 : 0;
+        a.lag = c->sb_lag;
         a.acc = (fuse && last) ? acc : nullptr;
         a.norm_part = (fuse && last && norm_slot) ? c->part : nullptr;
         a.ticket = c->tickets + i;
         if (i == 0) {
-            if (c->ws_sbits_active != w.sbits) {
+            if (c->ws_sbits_active != w.sbits * 16 + w.tb) {
                 // the counters are cumulative per super-block: a new block size starts a new count
                 CU(cudaMemsetAsync(c->sb_done, 0, ((size_t)(c->dim >> 13) + 1) * sizeof(unsigned long long), c->stream));
                 c->ws_epoch = 0;
-                c->ws_sbits_active = w.sbits;
+                c->ws_sbits_active = w.sbits * 16 + w.tb;
             }
             c->ws_epoch++;
-            a.done_target = c->ws_epoch << (w.sbits - kTileBits);
+            a.done_target = c->ws_epoch << (w.sbits - w.tb);
         }
-        hpsi_ws_kernel<<<grid, kWsThreads, kWsSmemBytes, c->stream>>>(a);
+        // strided tiles: tensor-map TMA when a row fits one box (<= 256 doubles) and there are rows at all
+        a.use_tmap = (c->use_tmap && g.hb > 0 && g.lb <= 7) ? 1 : 0;
+        CUtensorMap dummy;
+        memset(&dummy, 0, sizeof(dummy));
+        const CUtensorMap* tm = &dummy;
+        if (a.use_tmap) TRY(get_tmap(c, x, g.lb, g.hb, g.hb0, &tm));
+        if (w.tb == 11) hpsi_ws_kernel<11><<<grid, kWsThreads, kWsSmemBytes, c->stream>>>(a, *tm);
+        else hpsi_ws_kernel<12><<<grid, kWsThreads, kWsSmemBytes, c->stream>>>(a, *tm);
         LAUNCHED(c);
         TRY(check_launch(c, "hpsi_ws_kernel"));
     }
@@ -673,7 +734,8 @@ int qsb_create_sharded(int n_qubits, int device, int rank, int nranks, const voi
         CUB(cudaFuncSetAttribute(hpsi_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
         CUB(cudaFuncSetAttribute(hpsi_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
         CUB(cudaFuncSetAttribute(hpsi_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
-        CUB(cudaFuncSetAttribute(hpsi_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes));
+        CUB(cudaFuncSetAttribute(hpsi_ws_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes));
+        CUB(cudaFuncSetAttribute(hpsi_ws_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes));
         CUB(cudaMalloc(&c->tickets, 16 * sizeof(unsigned int)));
         {
             const size_t n_done = (size_t)(c->dim >> 13) + 1;
@@ -776,6 +838,14 @@ int qsb_set_option(qsb_ctx* c, const char* key, double value) {
         c->path = (int)value;
         c->force_flat = c->path == 1;
         c->plan = make_plan(c->nl, c->force_flat);
+    } else if (!strcmp(key, "tensor_map")) {
+        c->use_tmap = value != 0.0;
+    } else if (!strcmp(key, "tile_bits")) {
+        if (value != 0.0 && value != 11.0 && value != 12.0) return fail(c, QSB_ERR_INVALID, "tile_bits must be 0, 11 or 12");
+        c->ws_tile_bits = (int)value;
+    } else if (!strcmp(key, "sb_lag")) {
+        if (value < 0 || value > 64) return fail(c, QSB_ERR_INVALID, "sb_lag must be in 0..64");
+        c->sb_lag = (int)value;
     } else if (!strcmp(key, "sb_bits")) {
         if (value < 13 || value > 21) return fail(c, QSB_ERR_INVALID, "sb_bits must be in 13..21");
         c->sb_bits = (int)value;
@@ -1131,7 +1201,7 @@ int qsb_get_metrics(const qsb_ctx* c, qsb_metrics* out) {
     out->hpsi_passes = c->plan.n_pass;
     out->hpsi_bytes_per_amp = c->plan.bytes_per_amp;
     if (c->path == 0 && c->nl > kTileBits) {
-        const WsPlan w = make_ws_plan(c->nl, c->sb_bits);
+        const WsPlan w = make_ws_plan(c->nl, c->sb_bits, c->ws_tile_bits);
         out->hpsi_passes = 1 + w.n_plain;  // launches; the first one fuses two sub-passes through L2
         out->hpsi_bytes_per_amp = w.bytes_per_amp;
     }

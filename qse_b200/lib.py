@@ -14,7 +14,7 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libqsb.so")
+LIB_PATH = os.environ.get("QSB_LIB") or os.path.join(HERE, "libqsb.so")  # QSB_LIB: developer A/B builds
 NCCL_UID_BYTES = 128
 
 _c_double_p = C.POINTER(C.c_double)
