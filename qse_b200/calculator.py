@@ -386,7 +386,8 @@ class B200(_Base):
         if n < (1 << 18):
             return None
         buf = getattr(self, "_pinned", None)
-        if buf is None or buf.size != n or sys.getrefcount(buf) > 2:
+        # 3 = the attribute, the local name and getrefcount's own argument: nobody else holds it
+        if buf is None or buf.size != n or sys.getrefcount(buf) > 3:
             buf = lib.pinned_empty(n)
             self._pinned = buf
         return buf
