@@ -46,9 +46,9 @@ struct qsb_ctx {
     HpsiPlan plan;
     // warp-specialised super-block path (hpsi_ws.cuh)
     int path = 0;       // 0 auto (ws when N_local >= 13), 1 untiled, 2 one launch per tile-bit group
-    int sb_lag = 3;     // lead of the FIRST tiles over the INNER tiles of the fused launch, in super-blocks
+    int sb_lag = 0;     // lead of the FIRST tiles over the INNER tiles of the fused launch, in super-blocks
     int ws_tile_bits = 12;  // 12 (64 KiB tiles, 3 stages; measured best) or 11 (32 KiB tiles, 6 stages, two groups); 0 = fewest launches
-    int sb_bits = 18;   // log2 of the L2-resident super-block (10 MiB each; 18 / lead 3 measured best on B200)
+    int sb_bits = 0;   // log2 of the L2-resident super-block (10 MiB each; 18 / lead 3 measured best on B200)
     unsigned int* tickets = nullptr;        // one work counter per launch of an H psi
     unsigned long long* sb_done = nullptr;  // per super-block completion counters (cumulative)
     unsigned long long ws_epoch = 0;
@@ -183,7 +183,14 @@ static WsPlan make_ws_plan_tb(int nl, int sb_bits, int tb) {
     }
     return w;
 }
+// Measured on B200 (tools/ab_hpsi.py): the super-block must leave at most 9 index bits to the
+// plain launch (else a third trip to HBM), 2^18 amplitudes (10 MiB of x+y+E) with a lead of 3 blocks
+// is best while that holds (N_local <= 27); larger blocks want a shorter lead to stay inside L2.
+static int auto_sb_bits(int nl) { return std::max(18, std::min(21, nl - 9)); }
+static int auto_sb_lag(int sbits) { return sbits <= 18 ? 3 : (sbits == 19 ? 2 : 1); }
+
 static WsPlan make_ws_plan(int nl, int sb_bits, int tile_bits) {
+    if (sb_bits == 0) sb_bits = auto_sb_bits(nl);
     if (tile_bits == 11 || tile_bits == 12) return make_ws_plan_tb(nl, sb_bits, tile_bits);
     const WsPlan a = make_ws_plan_tb(nl, sb_bits, 11), b = make_ws_plan_tb(nl, sb_bits, 12);
     return (a.n_plain <= b.n_plain) ? a : b;
@@ -255,7 +262,7 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, double omega
         a.hb = g.hb;
         a.hb0 = g.hb0;
         a.last = last ? 1 : 0;
-        a.lag = c->sb_lag;
+        a.lag = c->sb_lag > 0 ? c->sb_lag : auto_sb_lag(w.sbits);
         a.acc = (fuse && last) ? acc : nullptr;
         a.norm_part = (fuse && last && norm_slot) ? c->part : nullptr;
         a.ticket = c->tickets + i;
@@ -847,7 +854,7 @@ int qsb_set_option(qsb_ctx* c, const char* key, double value) {
         if (value < 0 || value > 64) return fail(c, QSB_ERR_INVALID, "sb_lag must be in 0..64");
         c->sb_lag = (int)value;
     } else if (!strcmp(key, "sb_bits")) {
-        if (value < 13 || value > 21) return fail(c, QSB_ERR_INVALID, "sb_bits must be in 13..21");
+        if (value != 0.0 && (value < 13 || value > 21)) return fail(c, QSB_ERR_INVALID, "sb_bits must be 0 (auto) or in 13..21");
         c->sb_bits = (int)value;
     } else {
         return fail(c, QSB_ERR_INVALID, "unknown option '%s'", key);

@@ -385,3 +385,60 @@ def test_full_size_25_qubits_properties():
             eng.set_state(psi)
             outs.append(eng.apply_h(OMEGA_MAX, -1.5))
     assert np.max(np.abs(outs[0] - outs[1])) <= 1e-13 * np.max(np.abs(outs[1]))
+
+
+# ---- BASELINE configs 3 and 5 at full size: size-independent properties --------------------------
+def test_config5_random_28_qubits_bitstrings():
+    """BASELINE config 5: 28 random-position qubits (unit-disk register), detuning sweep, bit-string
+    probabilities read out on the device (the host never sees the 4 GiB state)."""
+    n = 28
+    reg = qb.lattices.random_register(n, 0.9 * qb.blockade_radius(OMEGA_MAX), seed=20261019)
+    t = 4
+    amp = qb.Signal(np.full(t, OMEGA_MAX), 4 * t)
+    det = qb.Signal(np.linspace(-OMEGA_MAX, 2 * OMEGA_MAX, t), 4 * t)
+    calc = qb.B200(reg, amp, det, return_state=False)
+    out = calc.calculate()
+    assert "state" not in out
+    eng = calc._engine
+    assert abs(eng.norm() - 1.0) < 1e-11
+    top = calc.bitstring_probabilities(8)
+    probs = [p for _, p in top]
+    assert all(len(b) == n for b, _ in top)
+    assert probs == sorted(probs, reverse=True) and 0 < sum(probs) <= 1.0 + 1e-12
+    assert top[0][0] == "0" * n  # 16 ns is far too short to leave |0...0> behind
+    number = calc.get_number_operator()
+    assert np.all(number > 0) and np.all(number < 0.5)
+    assert np.max(np.abs(calc.spins[:, 2] - (1 - 2 * number))) < 1e-12  # <Z> = 1 - 2<n>
+    # time reversal on the device returns to |0...0>
+    om, de, dt = qb.flatten_schedule(calc.amplitude, calc.detuning)
+    eng.evolve_schedule(om[::-1], de[::-1], -dt[::-1])
+    idx, p = eng.topk(1)
+    assert int(idx[0]) == 0 and 1.0 - p[0] <= INFID_TOL
+    calc.close()
+
+
+def test_config3_kagome_30_qubits_quench():
+    """BASELINE config 3: kagome 5x2 (30 qubits) quench at constant Omega, delta = 0 on ONE GPU
+    (16 GiB state): norm, symmetry of the lattice in <n_i>, and an exact time-reversal round trip."""
+    n = 30
+    qbits = qb.lattices.kagome(0.9 * qb.blockade_radius(OMEGA_MAX), 5, 2)
+    assert qbits.nqbits == n
+    with lib.Engine(n) as eng:
+        eng.set_interaction(qb.interaction_matrix(qbits.positions))
+        m = eng.metrics()
+        assert m["hpsi_passes"] == 2 and m["hpsi_bytes_per_amp"] == 88.0
+        om, de, dt = np.full(2, OMEGA_MAX), np.zeros(2), np.full(2, 0.002)
+        eng.evolve_schedule(om, de, dt)
+        assert abs(eng.norm() - 1.0) < 1e-11
+        number = eng.number()
+        assert np.all(number > 0) and np.all(number < 0.1)
+        # sites related by the inversion symmetry of the finite kagome patch evolve identically
+        pos = qbits.positions
+        centre = pos.mean(axis=0)
+        for i in range(n):
+            j = int(np.argmin(np.linalg.norm(pos - (2 * centre - pos[i]), axis=1)))
+            if np.linalg.norm(pos[j] - (2 * centre - pos[i])) < 1e-9:
+                assert abs(number[i] - number[j]) < 1e-12
+        eng.evolve_schedule(om, de, -dt)
+        idx, p = eng.topk(1)
+        assert int(idx[0]) == 0 and 1.0 - p[0] <= INFID_TOL
