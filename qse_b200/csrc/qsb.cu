@@ -17,6 +17,7 @@
 #include "hpsi_ws.cuh"
 #include "nccl_dl.h"
 #include "observe.cuh"
+#include "small.cuh"
 
 using namespace qsb;
 
@@ -53,6 +54,9 @@ struct qsb_ctx {
     unsigned long long* sb_done = nullptr;  // per super-block completion counters (cumulative)
     unsigned long long ws_epoch = 0;
     int ws_sbits_active = -1;
+    int small_kernel = 1;  // option "small_kernel": whole-schedule single-CTA kernel for N <= 12
+    double* sched_dev = nullptr;  // device copy of a schedule (small kernel)
+    size_t sched_cap = 0;
     int use_tmap = 1;  // option "tensor_map": 2-D tensor-map TMA for strided tiles (0 = one bulk copy per row)
     struct TmapEntry {
         const void* ptr;
@@ -456,6 +460,79 @@ static int evolve_segment_impl(qsb_ctx* c, double omega, double delta, double dt
 }
 
 // ------------------------------------------------------------------------------------------------
+// launch-bound sizes: the whole schedule in one single-CTA kernel (small.cuh)
+// ------------------------------------------------------------------------------------------------
+static bool small_schedule_ok(const qsb_ctx* c, const qsb_eops* eops) {
+    if (!c->small_kernel || c->nranks != 1 || c->nl > kSmallMaxQubits) return false;
+    if (eops)
+        for (int o = 0; o < eops->n_ops; ++o)
+            if (eops->ops[o].kind != QSB_EOP_ENERGY) return false;
+    return true;
+}
+
+static int evolve_schedule_small(qsb_ctx* c, const double* omega, const double* delta, const double* dt_us,
+                                 int64_t n_steps, const qsb_eops* eops, double* expectations_out) {
+    const int n_ops = eops ? eops->n_ops : 0;
+    // one device buffer: omega | delta | dt | eop_omega | eop_delta | expectations | info
+    const size_t n_sched = 3 * (size_t)n_steps, n_eop = 2 * (size_t)n_ops, n_exp = (size_t)n_steps * n_ops, n_info = 8;
+    const size_t need = n_sched + n_eop + n_exp + n_info;
+    if (need > c->sched_cap) {
+        cudaFree(c->sched_dev);
+        c->sched_dev = nullptr;
+        c->sched_cap = 0;
+        CU(cudaMalloc(&c->sched_dev, need * sizeof(double)));
+        c->sched_cap = need;
+    }
+    std::vector<double> host(n_sched + n_eop);
+    memcpy(host.data(), omega, n_steps * sizeof(double));
+    memcpy(host.data() + n_steps, delta, n_steps * sizeof(double));
+    memcpy(host.data() + 2 * n_steps, dt_us, n_steps * sizeof(double));
+    for (int o = 0; o < n_ops; ++o) {
+        host[n_sched + o] = eops->ops[o].omega;
+        host[n_sched + n_ops + o] = eops->ops[o].delta;
+    }
+    CU(cudaMemcpyAsync(c->sched_dev, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    SmallArgs a{};
+    a.psi = c->psi;
+    a.eint = c->eint;
+    a.omega = c->sched_dev;
+    a.delta = c->sched_dev + n_steps;
+    a.dt = c->sched_dev + 2 * n_steps;
+    a.n_steps = n_steps;
+    a.n = c->nl;
+    a.tol = c->tol;
+    a.theta_max = c->theta_max;
+    a.max_terms = c->max_terms;
+    a.fixed_terms = c->fixed_terms;
+    a.diag_min = c->diag_min;
+    a.diag_max = c->diag_max;
+    a.n_eops = n_ops;
+    a.eop_omega = c->sched_dev + n_sched;
+    a.eop_delta = c->sched_dev + n_sched + n_ops;
+    a.expect_out = c->sched_dev + n_sched + n_eop;
+    a.info = reinterpret_cast<unsigned long long*>(c->sched_dev + n_sched + n_eop + n_exp);
+    const size_t smem = 3 * sizeof(double2) << c->nl;
+    evolve_small_kernel<<<1, kSmallThreads, smem, c->stream>>>(a);
+    LAUNCHED(c);
+    TRY(check_launch(c, "evolve_small_kernel"));
+    std::vector<double> back(n_exp + n_info);
+    CU(cudaMemcpyAsync(back.data(), a.expect_out, back.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    unsigned long long info[8];
+    memcpy(info, back.data() + n_exp, sizeof(info));
+    c->met.hpsi_calls += info[0];
+    c->met.substeps += info[1];
+    c->met.segments += (uint64_t)n_steps;
+    c->met.last_terms = (int32_t)info[2];
+    c->m_prev = (int)info[2];
+    if (info[3] == 2) return fail(c, QSB_ERR_NOCONV, "Taylor term is NaN at step %llu", info[4]);
+    if (info[3] == 1)
+        return fail(c, QSB_ERR_NOCONV, "Taylor series did not reach tol=%.1e in %d terms at step %llu", c->tol, c->max_terms, info[4]);
+    if (n_exp) memcpy(expectations_out, back.data(), n_exp * sizeof(double));
+    return QSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // observables
 // ------------------------------------------------------------------------------------------------
 struct TermResult {
@@ -744,6 +821,7 @@ int qsb_create_sharded(int n_qubits, int device, int rank, int nranks, const voi
         CUB(cudaFuncSetAttribute(hpsi_ws_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes));
         CUB(cudaFuncSetAttribute(hpsi_ws_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes));
         CUB(cudaMalloc(&c->tickets, 16 * sizeof(unsigned int)));
+        CUB(cudaFuncSetAttribute(evolve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (int)sizeof(double2) << kSmallMaxQubits));
         {
             const size_t n_done = (size_t)(c->dim >> 13) + 1;
             CUB(cudaMalloc(&c->sb_done, n_done * sizeof(unsigned long long)));
@@ -795,6 +873,7 @@ int qsb_destroy(qsb_ctx* c) {
     cudaFree(c->flush_buf);
     cudaFree(c->topk_buf);
     cudaFree(c->tickets);
+    cudaFree(c->sched_dev);
     cudaFree(c->sb_done);
     if (c->h_slots) cudaFreeHost(c->h_slots);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -845,6 +924,8 @@ int qsb_set_option(qsb_ctx* c, const char* key, double value) {
         c->path = (int)value;
         c->force_flat = c->path == 1;
         c->plan = make_plan(c->nl, c->force_flat);
+    } else if (!strcmp(key, "small_kernel")) {
+        c->small_kernel = value != 0.0;
     } else if (!strcmp(key, "tensor_map")) {
         c->use_tmap = value != 0.0;
     } else if (!strcmp(key, "tile_bits")) {
@@ -988,6 +1069,7 @@ int qsb_evolve_schedule(qsb_ctx* c, const double* omega, const double* delta, co
     const int n_ops = eops ? eops->n_ops : 0;
     if (n_ops > 0 && !expectations_out) return fail(c, QSB_ERR_INVALID, "expectations_out is NULL");
     CU(cudaSetDevice(c->device));
+    if (n_steps > 0 && small_schedule_ok(c, eops)) return evolve_schedule_small(c, omega, delta, dt_us, n_steps, eops, expectations_out);
     std::vector<TermResult> res;
     for (int64_t s = 0; s < n_steps; ++s) {
         TRY(evolve_segment_impl(c, omega[s], delta[s], dt_us[s], nullptr));

@@ -442,3 +442,40 @@ def test_config3_kagome_30_qubits_quench():
         eng.evolve_schedule(om, de, -dt)
         idx, p = eng.topk(1)
         assert int(idx[0]) == 0 and 1.0 - p[0] <= INFID_TOL
+
+
+# ---- launch-bound sizes: whole-schedule kernel vs the multi-kernel stepper ------------------------
+@pytest.mark.parametrize("n", [1, 5, 9, 12])
+def test_small_schedule_kernel_matches_general_path(n):
+    reg = qb.lattices.random_register(n, 0.8 * qb.blockade_radius(OMEGA_MAX), seed=40 + n) if n > 1 \
+        else qb.Qbits(np.zeros((1, 2)))
+    t = 30
+    om = np.linspace(0.0, OMEGA_MAX, t)
+    de = np.linspace(-2 * OMEGA_MAX, 2 * OMEGA_MAX, t)
+    dt = np.full(t, 0.004)
+    dt[7] = 0.25  # one long segment: sub-stepping inside the kernel
+    states, exps, hpsi = [], [], []
+    for small in (1, 0):
+        with lib.Engine(n) as eng:
+            eng.set_option("small_kernel", small)
+            eng.set_interaction(qb.interaction_matrix(reg.positions))
+            eops = lib.PackedEops([("energy", 0.0, -2 * OMEGA_MAX), ("energy", OMEGA_MAX, 2 * OMEGA_MAX)])
+            m0 = eng.metrics()
+            exps.append(eng.evolve_schedule(om, de, dt, eops))
+            m1 = eng.metrics()
+            states.append(eng.get_state())
+            hpsi.append(m1["hpsi_calls"] - m0["hpsi_calls"])
+            launches = m1["kernel_launches"] - m0["kernel_launches"]
+            assert (launches == 1) == bool(small)
+            assert m1["substeps"] - m0["substeps"] > t
+    assert np.max(np.abs(states[0] - states[1])) <= 1e-12
+    assert np.max(np.abs(exps[0] - exps[1])) <= 1e-10 * max(1.0, np.max(np.abs(exps[1])))
+    assert hpsi[0] == hpsi[1] - 2 * t  # same Taylor term counts (the general path spends 2 H psi per step on e_ops)
+
+
+def test_small_schedule_kernel_reports_failure():
+    with lib.Engine(3) as eng:
+        eng.set_interaction(np.zeros((3, 3)))
+        eng.set_option("max_terms", 2)
+        with pytest.raises(lib.QsbError, match="did not reach tol"):
+            eng.evolve_schedule(np.array([5.0]), np.array([1.0]), np.array([0.5]))
