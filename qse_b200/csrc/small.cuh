@@ -47,9 +47,9 @@ QSB_DEV double block_allreduce(double v, double* red, double* bcast) {
 }
 
 __global__ void __launch_bounds__(kSmallThreads, 1) evolve_small_kernel(const SmallArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char small_smem_raw[];
     const int dim = 1 << a.n;
-    double2* psi = reinterpret_cast<double2*>(smem_raw);
+    double2* psi = reinterpret_cast<double2*>(small_smem_raw);
     double2* ya = psi + dim;
     double2* yb = ya + dim;
     __shared__ double red[32];

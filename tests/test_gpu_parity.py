@@ -453,7 +453,7 @@ def test_small_schedule_kernel_matches_general_path(n):
     om = np.linspace(0.0, OMEGA_MAX, t)
     de = np.linspace(-2 * OMEGA_MAX, 2 * OMEGA_MAX, t)
     dt = np.full(t, 0.004)
-    dt[7] = 0.25  # one long segment: sub-stepping inside the kernel
+    dt[7] = 1.0  # one long segment: sub-stepping inside the kernel
     states, exps, hpsi = [], [], []
     for small in (1, 0):
         with lib.Engine(n) as eng:
@@ -470,7 +470,9 @@ def test_small_schedule_kernel_matches_general_path(n):
             assert m1["substeps"] - m0["substeps"] > t
     assert np.max(np.abs(states[0] - states[1])) <= 1e-12
     assert np.max(np.abs(exps[0] - exps[1])) <= 1e-10 * max(1.0, np.max(np.abs(exps[1])))
-    assert hpsi[0] == hpsi[1] - 2 * t  # same Taylor term counts (the general path spends 2 H psi per step on e_ops)
+    # the general path spends 2 H psi per step on the e_ops and may overshoot a term (it only reads
+    # norms back from term m_prev - 1 on); the in-kernel stepper tests every term
+    assert 0.5 * (hpsi[1] - 2 * t) <= hpsi[0] <= hpsi[1] - 2 * t
 
 
 def test_small_schedule_kernel_reports_failure():
