@@ -53,7 +53,7 @@ struct WsCfg {
 };
 constexpr int kMaxStages = 12;
 
-enum { kItemFirst = 0, kItemInner = 1, kItemPlain = 2, kItemDone = 3 };
+enum { kItemFirst = 0, kItemInner = 1, kItemPlain = 2, kItemDone = 3, kItemPeer = 4 };
 
 struct WsItem {
     u64 base;
@@ -98,8 +98,9 @@ QSB_DEV u64 ws_tile_base(int lb, int hb, int hb0, u64 tau) {
 // address.  Global operands (E_int or partial y, the Taylor accumulator, the first NVLink partner)
 // are requested up front with loads the compiler may not sink, so their latency hides behind the
 // shared-memory flip phase.
-// PEER (FIRST only): sharded-qubit partners are read over NVLink; x is then re-read from the tile
-// at the end instead of being kept live, to make room for the partner amplitudes in flight.
+// PEER (FIRST only, sharded state): the producer has already pulled the partner tiles over NVLink
+// (kItemPeer stages, ws_peer below) and y holds (omega/2) * their sum; x is re-read from the tile at
+// the end instead of being kept live.
 template <int TB, bool FIRST, bool PEER>
 QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 base, bool last, int t, double& nrm) {
     using C = WsCfg<TB>;
@@ -117,7 +118,7 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
     for (int j = 0; j < kPerThread; ++j) {
         if (FIRST) {
             e[j] = ldnc1(p.eint + QSB_GADDR(j));
-            if (PEER) yv[j] = ldg2_volatile(p.peer[0] + QSB_GADDR(j));  // over NVLink
+            if (PEER) yv[j] = ldcg2(p.y + QSB_GADDR(j));  // (omega/2) * sum of partner amplitudes, left by the PEER items
         } else {
             yv[j] = ldcg2(p.y + QSB_GADDR(j));
         }
@@ -152,17 +153,6 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
 #pragma unroll
             for (int j = 0; j < kPerThread; ++j) cacc(sum[j], ts[tb + j * C::kGroupThreads]);
         }
-        if (PEER) {
-#pragma unroll
-            for (int j = 0; j < kPerThread; ++j) cacc(sum[j], yv[j]);
-        }
-        for (int q = 1; PEER && q < p.n_peer; ++q) {
-            const double2* __restrict__ px = p.peer[q];
-#pragma unroll
-            for (int j = 0; j < kPerThread; ++j) yv[j] = ldg2_volatile(px + QSB_GADDR(j));
-#pragma unroll
-            for (int j = 0; j < kPerThread; ++j) cacc(sum[j], yv[j]);
-        }
     } else {
         for (int b = act_lo; b < C::kRegLo; ++b) {
             const int tb = t ^ (1 << b);
@@ -178,6 +168,7 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
             const double d = e[j] - p.delta * (double)(__popcll(g) + p.pop_rank);
             const double2 xj = PEER ? ts[QSB_IDX(j)] : yv[j];
             v = make_double2(d * xj.x + p.half_omega * sum[j].x, d * xj.y + p.half_omega * sum[j].y);
+            if (PEER) cacc(v, yv[j]);
         } else {
             v = make_double2(yv[j].x + p.half_omega * sum[j].x, yv[j].y + p.half_omega * sum[j].y);
         }
@@ -190,6 +181,24 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
     }
 #undef QSB_GADDR
 #undef QSB_IDX
+}
+
+// A partner GPU's tile (the sharded-qubit flip of the same 2^TB amplitudes), pulled over NVLink by
+// the producer's TMA copies into an ordinary stage: y = (omega/2) * partner  (first partner) or
+// y += (omega/2) * partner.  The FIRST item of the same tile follows in the same CTA, so the same
+// thread re-reads what it wrote: program order is the only synchronisation needed, and no consumer
+// ever stalls on an NVLink load -- the transfer latency sits in the stage ring like any other tile.
+template <int TB>
+QSB_DEV void ws_peer(const HpsiWs& p, const double2* __restrict__ ts, u64 base, int q, int t) {
+    using C = WsCfg<TB>;
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+        const int idx = t + j * C::kGroupThreads;
+        const double2 v = ts[idx];
+        double2 out = make_double2(p.half_omega * v.x, p.half_omega * v.y);
+        if (q > 0) cacc(out, ldcg2(p.y + base + idx));
+        p.y[base + idx] = out;
+    }
 }
 
 template <int TB>
@@ -235,12 +244,19 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
             const u64 lag = p.fused ? ((u64)p.lag < n_sb ? (u64)(p.lag < 1 ? 1 : p.lag) : n_sb) : 0;
             const u64 total = p.fused ? 2ull * p.n_tiles : p.n_tiles;
             int n_done = 0;
+            int peer_left = 0;         // partner stages still to publish for the pending FIRST tile
+            bool first_pending = false;
+            u64 pend_tau = 0;
             for (u64 it = 0;; ++it) {
                 const int s = (int)(it % C::kStages);
                 const u64 use = it / C::kStages;
                 if (use > 0) mbar_wait(&empty_bar[s], (uint32_t)((use - 1) & 1ull));
                 int type = kItemDone;
                 u64 tau = 0;
+                if (peer_left > 0 || first_pending) {
+                    type = peer_left > 0 ? kItemPeer : kItemFirst;
+                    tau = pend_tau;
+                } else {
                 if (lane == 0 && n_done == 0) {
                     const u64 ticket = atomicAdd(p.ticket, 1u);
                     if (ticket < total) {
@@ -262,6 +278,35 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                 }
                 type = __shfl_sync(0xffffffffu, type, 0);
                 tau = __shfl_sync(0xffffffffu, tau, 0);
+                if (type == kItemFirst && p.n_peer > 0) {
+                    // sharded state: the partner tiles go first, one stage each, then the tile itself
+                    pend_tau = tau;
+                    peer_left = p.n_peer;
+                    first_pending = true;
+                    type = kItemPeer;
+                }
+                }
+                if (type == kItemPeer) {
+                    const int q = p.n_peer - peer_left;
+                    --peer_left;
+                    const u64 pbase = tau << TB;
+                    double2* pstage = tiles + (size_t)s * C::kTileW;
+                    if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(C::kTileW * sizeof(double2)));
+                    __syncwarp();
+                    constexpr int kCopies = 4;
+                    constexpr int chunk = C::kTileW / kCopies;
+                    if (lane < kCopies)  // TMA pull from the partner's HBM over NVLink
+                        bulk_g2s(pstage + lane * chunk, p.peer[q] + pbase + (u64)lane * chunk, chunk * sizeof(double2), &full_bar[s]);
+                    if (lane == 0) {
+                        desc[s].base = pbase;
+                        desc[s].type = kItemPeer;
+                        desc[s].sb = q;
+                        mbar_arrive(&full_bar[s]);
+                    }
+                    __syncwarp();
+                    continue;
+                }
+                first_pending = false;
                 if (type == kItemDone) {
                     // out of work: one sentinel per consumer group (consecutive items go to distinct groups)
                     if (lane == 0) {
@@ -343,6 +388,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                         atomicAdd(p.done + sb, 1ull);
                     }
                 }
+            } else if (type == kItemPeer) {
+                ws_peer<TB>(p, ts, base, sb, tg);
             } else {
                 ws_process<TB, false, false>(p, ts, base, p.last != 0, tg, nrm);
             }

@@ -240,7 +240,8 @@ static int get_tmap(qsb_ctx* c, const double2* x, int lb, int hb, int hb0, const
 // index bits above the super-block (hpsi_ws.cuh)
 static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, double omega, double delta, bool fuse,
                           double2 scale, double2* acc, double* norm_slot, const double2* const* peers) {
-    const WsPlan w = make_ws_plan(c->nl, c->sb_bits, c->ws_tile_bits);
+    // partner stages and their FIRST stage must be consumed by the same threads: one consumer group
+    const WsPlan w = make_ws_plan(c->nl, c->sb_bits, c->nranks > 1 ? 12 : c->ws_tile_bits);
     const u64 n_tiles = c->dim >> w.tb;
     const int grid = (int)std::min<u64>(n_tiles, (u64)c->n_sm);
     CU(cudaMemsetAsync(c->tickets, 0, 16 * sizeof(unsigned int), c->stream));
@@ -1290,7 +1291,7 @@ int qsb_get_metrics(const qsb_ctx* c, qsb_metrics* out) {
     out->hpsi_passes = c->plan.n_pass;
     out->hpsi_bytes_per_amp = c->plan.bytes_per_amp;
     if (c->path == 0 && c->nl > kTileBits) {
-        const WsPlan w = make_ws_plan(c->nl, c->sb_bits, c->ws_tile_bits);
+        const WsPlan w = make_ws_plan(c->nl, c->sb_bits, c->nranks > 1 ? 12 : c->ws_tile_bits);
         out->hpsi_passes = 1 + w.n_plain;  // launches; the first one fuses two sub-passes through L2
         out->hpsi_bytes_per_amp = w.bytes_per_amp;
     }
