@@ -481,3 +481,28 @@ def test_small_schedule_kernel_reports_failure():
         eng.set_option("max_terms", 2)
         with pytest.raises(lib.QsbError, match="did not reach tol"):
             eng.evolve_schedule(np.array([5.0]), np.array([1.0]), np.array([0.5]))
+
+
+@pytest.mark.parametrize("opts", [{"tile_bits": 11}, {"tensor_map": 0}, {"tile_bits": 11, "tensor_map": 0, "sb_bits": 16, "sb_lag": 2},
+                                  {"sb_bits": 21, "sb_lag": 1}])
+def test_kernel_options_do_not_change_results(opts):
+    """Every tuning knob of the H psi kernel (tile size, TMA flavour, super-block size / lead) is a
+    pure scheduling choice: same result as the untiled kernel, for H psi and for a short sweep."""
+    n = 22
+    pos = random_positions(n, 9)
+    psi = random_state(n, 9)
+    with lib.Engine(n) as eng:
+        eng.set_interaction(qb.interaction_matrix(pos))
+        eng.set_state(psi)
+        eng.set_option("hpsi_path", 1)
+        want = eng.apply_h(3.0, -1.0)
+        eng.evolve_schedule(np.array([2.0, 4.0]), np.array([-3.0, 3.0]), np.array([0.002, 0.002]))
+        ref_state = eng.get_state()
+        eng.set_option("hpsi_path", 0)
+        for key, value in opts.items():
+            eng.set_option(key, value)
+        eng.set_state(psi)
+        got = eng.apply_h(3.0, -1.0)
+        assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+        eng.evolve_schedule(np.array([2.0, 4.0]), np.array([-3.0, 3.0]), np.array([0.002, 0.002]))
+        assert np.max(np.abs(eng.get_state() - ref_state)) <= 1e-13
