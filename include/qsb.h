@@ -155,6 +155,11 @@ int qsb_probabilities(qsb_ctx* ctx, double* out);
  * idx are global basis indices.  docs/use-cases/adiabatic.ipynb cell 8. [collective] */
 int qsb_topk_probs(qsb_ctx* ctx, int k, uint64_t* idx, double* prob);
 
+/* `shots` basis states drawn from |psi_k|^2 / <psi|psi> (global basis indices, in draw order);
+ * deterministic in `seed`, identical on every rank.  The measurement read-out Pulser users get from
+ * results.sample_final_state (docs/tutorials/pulser-calc-example.ipynb cell 10). [collective] */
+int qsb_sample(qsb_ctx* ctx, uint64_t seed, int64_t shots, uint64_t* out);
+
 /* ---- measurement ------------------------------------------------------------------- */
 typedef struct {
     uint64_t hpsi_calls;        /* H psi applications since creation */

@@ -428,6 +428,17 @@ class B200(_Base):
 
         return structure_factor_from_sij(L1, L2, L3, self.qbits, self.sij)
 
+    def sample_final_state(self, shots: int = 1000, seed: int = 0):
+        """Measurement read-out: ``Counter({bitstring: count})`` of ``shots`` projective measurements
+        of the final state (what Pulser's ``results.sample_final_state`` returns; qubit 0 first)."""
+        from collections import Counter
+
+        if self.results is None:
+            self.calculate()
+        n = self._nqbits()
+        idx, counts = np.unique(self._engine.sample(shots, seed), return_counts=True)
+        return Counter({np.binary_repr(int(i), n): int(k) for i, k in zip(idx, counts)})
+
     def bitstring_probabilities(self, k: int = 16):
         """Top-k basis states as ``[(bitstring, probability), ...]`` (adiabatic.ipynb cell 8)."""
         if self.results is None:

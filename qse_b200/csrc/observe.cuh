@@ -215,4 +215,47 @@ __global__ void __launch_bounds__(256) gather_ge_kernel(const double2* __restric
     }
 }
 
+// ---- K7: sampling basis states from |psi|^2 ---------------------------------------------------------
+// chunk_sums[c] = sum of |psi_k|^2 over chunk c (2^cb amplitudes); one block per chunk (grid-stride)
+__global__ void __launch_bounds__(256) chunk_prob_kernel(const double2* __restrict__ psi, int cb, u64 n_chunks,
+                                                         double* __restrict__ chunk_sums) {
+    __shared__ double red[32];
+    const u64 len = 1ull << cb;
+    for (u64 c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        double s = 0.0;
+        for (u64 k = threadIdx.x; k < len; k += blockDim.x) s += cnorm2(psi[(c << cb) + k]);
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) chunk_sums[c] = s;
+    }
+}
+// one warp per shot: walk the chunk until the running sum of |psi|^2 passes the residual
+__global__ void __launch_bounds__(256) sample_resolve_kernel(const double2* __restrict__ psi, int cb, long long n,
+                                                             const u64* __restrict__ chunk, const double* __restrict__ resid,
+                                                             u64* __restrict__ out) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const u64 base = chunk[w] << cb, len = 1ull << cb;
+    const double r = resid[w];
+    double run = 0.0;
+    u64 found = ~0ull, last_nonzero = 0;
+    for (u64 k0 = 0; k0 < len && found == ~0ull; k0 += 32) {
+        const u64 k = k0 + lane;
+        const double pk = (k < len) ? cnorm2(psi[base + k]) : 0.0;
+        double inc = pk;  // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += up;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, pk > 0.0 && run + inc > r);
+        const unsigned nz = __ballot_sync(0xffffffffu, pk > 0.0);
+        if (nz) last_nonzero = k0 + (31 - __clz(nz));
+        if (hit) found = k0 + (__ffs(hit) - 1);
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (found == ~0ull) found = last_nonzero;  // rounding: the residual sat on the chunk's upper edge
+    if (lane == 0) out[w] = base + found;
+}
+
 }  // namespace qsb

@@ -1285,6 +1285,105 @@ int qsb_topk_probs(qsb_ctx* c, int k, uint64_t* idx, double* prob) {
     return QSB_OK;
 }
 
+static inline uint64_t splitmix64(uint64_t& x) {
+    uint64_t z = (x += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+int qsb_sample(qsb_ctx* c, uint64_t seed, int64_t shots, uint64_t* out) {
+    if (!c || !out || shots < 0) return fail(c, QSB_ERR_INVALID, "bad argument");
+    if (shots == 0) return QSB_OK;
+    CU(cudaSetDevice(c->device));
+    const int cb = std::min(c->nl, 12);
+    const u64 n_chunks = c->dim >> cb;
+    // scratch: chunk sums | per-shot (chunk, residual, result) -- carved from a dedicated allocation
+    const size_t need = n_chunks * sizeof(double) + (size_t)shots * 24 + (size_t)(c->nranks + shots) * sizeof(double);
+    if (need > c->topk_bytes) {
+        cudaFree(c->topk_buf);
+        c->topk_buf = nullptr;
+        c->topk_bytes = 0;
+        CU(cudaMalloc(&c->topk_buf, need));
+        c->topk_bytes = need;
+    }
+    double* d_sums = reinterpret_cast<double*>(c->topk_buf);
+    u64* d_chunk = reinterpret_cast<u64*>(d_sums + n_chunks);
+    double* d_resid = reinterpret_cast<double*>(d_chunk + shots);
+    u64* d_out = reinterpret_cast<u64*>(d_resid + shots);
+    double* d_comm = reinterpret_cast<double*>(d_out + shots);  // nranks + shots doubles
+    chunk_prob_kernel<<<(int)std::min<u64>(n_chunks, (u64)c->n_sm * 8), 256, 0, c->stream>>>(c->psi, cb, n_chunks, d_sums);
+    LAUNCHED(c);
+    TRY(check_launch(c, "chunk_prob_kernel"));
+    std::vector<double> sums(n_chunks);
+    CU(cudaMemcpyAsync(sums.data(), d_sums, n_chunks * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<double> cdf(n_chunks);
+    double mine = 0.0;
+    for (u64 i = 0; i < n_chunks; ++i) {
+        mine += sums[i];
+        cdf[i] = mine;
+    }
+    // every rank needs every shard's probability mass
+    std::vector<double> mass(c->nranks, 0.0);
+    mass[c->rank] = mine;
+    if (c->nranks > 1) {
+        CU(cudaMemcpyAsync(d_comm, mass.data(), c->nranks * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        TRY(allreduce(c, d_comm, (size_t)c->nranks, kNcclSum));
+        CU(cudaMemcpyAsync(mass.data(), d_comm, c->nranks * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    double total = 0.0;
+    std::vector<double> rank_lo(c->nranks + 1, 0.0);
+    for (int r = 0; r < c->nranks; ++r) {
+        total += mass[r];
+        rank_lo[r + 1] = total;
+    }
+    if (!(total > 0.0)) return fail(c, QSB_ERR_STATE, "cannot sample from a state of zero norm");
+    // same uniforms on every rank; each rank resolves the shots that land in its shard
+    std::vector<u64> h_chunk;
+    std::vector<double> h_resid;
+    std::vector<int64_t> h_slot;
+    uint64_t state = seed;
+    for (int64_t sidx = 0; sidx < shots; ++sidx) {
+        const double u = (double)(splitmix64(state) >> 11) * (1.0 / 9007199254740992.0) * total;
+        int r = (int)(std::upper_bound(rank_lo.begin() + 1, rank_lo.end(), u) - (rank_lo.begin() + 1));
+        if (r >= c->nranks) r = c->nranks - 1;
+        if (r != c->rank) continue;
+        const double local = u - rank_lo[r];
+        u64 ch = (u64)(std::upper_bound(cdf.begin(), cdf.end(), local) - cdf.begin());
+        if (ch >= n_chunks) ch = n_chunks - 1;
+        h_chunk.push_back(ch);
+        h_resid.push_back(local - (ch ? cdf[ch - 1] : 0.0));
+        h_slot.push_back(sidx);
+    }
+    const long long n_mine = (long long)h_chunk.size();
+    std::vector<u64> h_out((size_t)n_mine);
+    if (n_mine > 0) {
+        CU(cudaMemcpyAsync(d_chunk, h_chunk.data(), n_mine * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_resid, h_resid.data(), n_mine * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        const long long threads = n_mine * 32;
+        sample_resolve_kernel<<<(int)((threads + 255) / 256), 256, 0, c->stream>>>(c->psi, cb, n_mine, d_chunk, d_resid, d_out);
+        LAUNCHED(c);
+        TRY(check_launch(c, "sample_resolve_kernel"));
+        CU(cudaMemcpyAsync(h_out.data(), d_out, n_mine * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    if (c->nranks == 1) {
+        for (long long i = 0; i < n_mine; ++i) out[h_slot[i]] = h_out[i];
+        return QSB_OK;
+    }
+    // merge: basis indices < 2^53 are exact in float64, every shot is owned by exactly one rank
+    std::vector<double> merged((size_t)shots, 0.0);
+    for (long long i = 0; i < n_mine; ++i) merged[h_slot[i]] = (double)(c->rank_bits + h_out[i]);
+    CU(cudaMemcpyAsync(d_comm, merged.data(), (size_t)shots * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    TRY(allreduce(c, d_comm, (size_t)shots, kNcclSum));
+    CU(cudaMemcpyAsync(merged.data(), d_comm, (size_t)shots * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < shots; ++i) out[i] = (uint64_t)merged[i];
+    return QSB_OK;
+}
+
 int qsb_get_metrics(const qsb_ctx* c, qsb_metrics* out) {
     if (!c || !out) return fail(nullptr, QSB_ERR_INVALID, "NULL argument");
     *out = c->met;

@@ -79,6 +79,7 @@ SIGNATURES = {
     "qsb_number": (C.c_int, [_ctx_p, _c_double_p]),
     "qsb_probabilities": (C.c_int, [_ctx_p, _c_double_p]),
     "qsb_topk_probs": (C.c_int, [_ctx_p, C.c_int, _c_u64_p, _c_double_p]),
+    "qsb_sample": (C.c_int, [_ctx_p, C.c_uint64, C.c_int64, _c_u64_p]),
     "qsb_get_metrics": (C.c_int, [_ctx_p, C.POINTER(QsbMetrics)]),
     "qsb_time_apply_h": (C.c_int, [_ctx_p, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "qsb_time_schedule": (C.c_int, [_ctx_p, _c_double_p, _c_double_p, _c_double_p, C.c_int64,
@@ -316,6 +317,12 @@ class Engine:
         p = np.empty(k, dtype=np.float64)
         self._check(self._lib.qsb_topk_probs(self._ctx, int(k), _up(idx), _dp(p)))
         return idx, p
+
+    def sample(self, shots: int, seed: int = 0) -> np.ndarray:
+        """`shots` basis indices drawn from |psi|^2 (uint64, in draw order; same on every rank)."""
+        out = np.empty(int(shots), dtype=np.uint64)
+        self._check(self._lib.qsb_sample(self._ctx, int(seed) & (2**64 - 1), int(shots), _up(out)))
+        return out
 
     # -- measurement -----------------------------------------------------------------------
     def metrics(self) -> dict:

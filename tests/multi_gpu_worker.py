@@ -72,6 +72,14 @@ def main():
                 prob = np.abs(psi) ** 2
                 order = np.lexsort((np.arange(prob.size), -prob))[:8]
                 check(f"n={n} topk", np.array_equal(idx, order.astype(np.uint64)) and np.allclose(p, prob[order], rtol=1e-15))
+            if exchange == "ipc":
+                shots = 50000
+                smp = eng.sample(shots, seed=17).astype(np.int64)
+                prob = np.abs(psi) ** 2
+                owner_freq = np.bincount(smp >> plan.nl, minlength=world) / shots
+                owner_p = prob.reshape(world, -1).sum(axis=1)
+                check(f"n={n} sampling across shards", bool(np.max(np.abs(owner_freq - owner_p)) < 6 * np.sqrt(0.25 / shots)
+                                                            and np.all(prob[smp] > 0)))
             d = float(np.max(np.abs(eng.number() - orc.get_number_operator(psi, n))))
             check(f"{exchange} n={n} number", d <= 1e-12, f"{d:.2e}")
             check(f"{exchange} n={n} norm", abs(eng.norm() - 1.0) <= 1e-12)

@@ -506,3 +506,41 @@ def test_kernel_options_do_not_change_results(opts):
         assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
         eng.evolve_schedule(np.array([2.0, 4.0]), np.array([-3.0, 3.0]), np.array([0.002, 0.002]))
         assert np.max(np.abs(eng.get_state() - ref_state)) <= 1e-13
+
+
+def test_sampling_follows_the_born_rule():
+    n = 10
+    psi = random_state(n, 321)
+    p = np.abs(psi) ** 2
+    with lib.Engine(n) as eng:
+        eng.set_state(psi)
+        shots = 400_000
+        a = eng.sample(shots, seed=7)
+        assert np.array_equal(a, eng.sample(shots, seed=7))  # deterministic in the seed
+        assert not np.array_equal(a, eng.sample(shots, seed=8))
+        freq = np.bincount(a.astype(np.int64), minlength=1 << n) / shots
+        # binomial standard error per bin: sqrt(p (1 - p) / shots) <= 5e-5 * ...; allow 6 sigma
+        assert np.all(np.abs(freq - p) <= 6 * np.sqrt(p * (1 - p) / shots) + 1e-6)
+        basis = np.zeros(1 << n, dtype=complex)
+        basis[0b1011001110] = 1.0
+        eng.set_state(basis)
+        assert np.all(eng.sample(100, seed=1) == 0b1011001110)
+    n = 14  # several chunks of 4096 amplitudes
+    psi = random_state(n, 5)
+    with lib.Engine(n) as eng:
+        eng.set_state(psi)
+        a = eng.sample(200_000, seed=3)
+        chunk_freq = np.bincount(a.astype(np.int64) >> 12, minlength=4) / a.size
+        chunk_p = (np.abs(psi) ** 2).reshape(4, -1).sum(axis=1)
+        assert np.max(np.abs(chunk_freq - chunk_p)) < 6 * np.sqrt(0.25 / a.size)
+
+
+def test_calculator_sample_final_state():
+    qbits = qb.lattices.chain(0.9 * qb.blockade_radius(OMEGA_MAX), 4)
+    calc = qb.B200(qbits, qb.Signal([OMEGA_MAX], 200), qb.Signal([0.0], 200))
+    counts = calc.sample_final_state(shots=5000, seed=11)
+    assert sum(counts.values()) == 5000 and all(len(b) == 4 for b in counts)
+    p = np.abs(calc.statevector) ** 2
+    top = max(counts, key=counts.get)
+    assert int(top, 2) == int(np.argmax(p))
+    calc.close()
