@@ -142,3 +142,13 @@ QSB_DEV void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1, uint6
         "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+
+// L2 prefetches issued by the producer warp for everything the consumers will read with plain
+// loads (E_int, partial y, the accumulator): the loads then hit L2 instead of waiting on HBM
+QSB_DEV void prefetch_l2(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+QSB_DEV void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1)
+                 : "memory");
+}

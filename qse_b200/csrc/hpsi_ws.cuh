@@ -141,11 +141,6 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
             for (int j = 0; j < kPerThread; ++j) yv[j] = xv[j];
         }
     }
-    double2 accv[kPerThread];
-    if (with_acc) {
-#pragma unroll
-        for (int j = 0; j < kPerThread; ++j) accv[j] = ldg2_volatile(p.acc + QSB_GADDR(j));
-    }
     if (FIRST) {
 #pragma unroll
         for (int b = 0; b < C::kRegLo; ++b) {
@@ -159,6 +154,13 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
 #pragma unroll
             for (int j = 0; j < kPerThread; ++j) cacc(sum[j], ts[tb + j * C::kGroupThreads]);
         }
+    }
+    // the accumulator was prefetched into L2 by the producer: load it only now (loading it before
+    // the flip phase made the compiler spill it, and the spill store waited on HBM)
+    double2 accv[kPerThread];
+    if (with_acc) {
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) accv[j] = ldg2_volatile(p.acc + QSB_GADDR(j));
     }
 #pragma unroll
     for (int j = 0; j < kPerThread; ++j) {
@@ -202,7 +204,9 @@ QSB_DEV void ws_peer(const HpsiWs& p, const double2* __restrict__ ts, u64 base, 
 }
 
 template <int TB>
-__global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, const __grid_constant__ CUtensorMap tmap,
+                                                                const __grid_constant__ CUtensorMap tmap_y,
+                                                                const __grid_constant__ CUtensorMap tmap_acc) {
     using C = WsCfg<TB>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2* tiles = reinterpret_cast<double2*>(smem_raw);
@@ -323,10 +327,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                 __syncwarp();
                 if (type == kItemFirst) {
                     base = tau << TB;
-                    constexpr int kCopies = 4;  // per-copy overhead of the TMA engine favours few large copies
+#ifndef QSB_WS_COPIES
+#define QSB_WS_COPIES 4
+#endif
+                    constexpr int kCopies = QSB_WS_COPIES;  // per-copy overhead of the TMA engine favours few large copies
                     constexpr int chunk = C::kTileW / kCopies;
                     if (lane < kCopies)
                         bulk_g2s(stage + lane * chunk, p.x + base + (u64)lane * chunk, chunk * sizeof(double2), &full_bar[s]);
+                    if (lane == kCopies) prefetch_l2(p.eint + base, (uint32_t)(C::kTileW * sizeof(double)));
                 } else {
                     base = ws_tile_base(p.lb, p.hb, p.hb0, tau);
                     const int rows = 1 << p.hb;
@@ -336,8 +344,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                         const int mid_bits = p.hb0 - p.lb;
                         const int c0 = (int)((tau & ((1ull << mid_bits) - 1ull)) << (p.lb + 1));
                         const int c1 = (int)((tau >> mid_bits) << p.hb);
-                        if (lane < ((rows + 255) >> 8))
+                        const int n_box = (rows + 255) >> 8;
+                        if (lane < n_box)
                             tma_load_2d(stage + ((size_t)(lane * 256) << p.lb), &tmap, c0, c1 + lane * 256, &full_bar[s]);
+                        // the plain launch reads its partial y (and the accumulator) from HBM: start them now
+                        if (type == kItemPlain && lane >= 8 && lane < 8 + n_box) tma_prefetch_2d(&tmap_y, c0, c1 + (lane - 8) * 256);
+                        if (type == kItemPlain && p.last && p.acc != nullptr && lane >= 16 && lane < 16 + n_box)
+                            tma_prefetch_2d(&tmap_acc, c0, c1 + (lane - 16) * 256);
                     } else {
                         const uint32_t row_bytes = (uint32_t)(sizeof(double2) << p.lb);
                         for (int r = lane; r < rows; r += 32)

@@ -286,9 +286,19 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, double omega
         CUtensorMap dummy;
         memset(&dummy, 0, sizeof(dummy));
         const CUtensorMap* tm = &dummy;
-        if (a.use_tmap) TRY(get_tmap(c, x, g.lb, g.hb, g.hb0, &tm));
-        if (w.tb == 11) hpsi_ws_kernel<11><<<grid, kWsThreads, kWsSmemBytes, c->stream>>>(a, *tm);
-        else hpsi_ws_kernel<12><<<grid, kWsThreads, kWsSmemBytes, c->stream>>>(a, *tm);
+        const CUtensorMap *tm_y = &dummy, *tm_acc = &dummy;
+        CUtensorMap tm_copy, tm_y_copy;  // get_tmap may grow the cache: copy before the next lookup
+        if (a.use_tmap) {
+            TRY(get_tmap(c, x, g.lb, g.hb, g.hb0, &tm));
+            tm_copy = *tm;
+            tm = &tm_copy;
+            TRY(get_tmap(c, y, g.lb, g.hb, g.hb0, &tm_y));
+            tm_y_copy = *tm_y;
+            tm_y = &tm_y_copy;
+            if (a.acc) TRY(get_tmap(c, a.acc, g.lb, g.hb, g.hb0, &tm_acc));
+        }
+        if (w.tb == 11) hpsi_ws_kernel<11><<<grid, kWsThreads, kWsSmemBytes, c->stream>>>(a, *tm, *tm_y, *tm_acc);
+        else hpsi_ws_kernel<12><<<grid, kWsThreads, kWsSmemBytes, c->stream>>>(a, *tm, *tm_y, *tm_acc);
         LAUNCHED(c);
         TRY(check_launch(c, "hpsi_ws_kernel"));
     }
