@@ -70,7 +70,8 @@ int qsb_local_dim(const qsb_ctx* ctx, uint64_t* dim);   /* 2^(N-p) amplitudes in
  * L2-resident super-block, 13..21; 0 = auto: 18..21 by shard size), "sb_lag" (lead, in
  * super-blocks, of the first sub-pass over the second inside the fused launch; 0 = auto),
  * "tile_bits" (12 or 11),
- * "tensor_map" (1 = strided tiles fetched with 2-D tensor-map TMA, 0 = one bulk copy per row) */
+ * "tensor_map" (1 = strided tiles fetched with 2-D tensor-map TMA, 0 = one bulk copy per row),
+ * "small_kernel" (1 = schedules of <= 12 qubits run in one single-block launch) */
 int qsb_set_option(qsb_ctx* ctx, const char* key, double value);
 
 /* page-locked host memory for state-sized transfers (qsb_get_state / qsb_set_state run at PCIe
