@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(256) finalize_pair_kernel(const double* part, 
 
 // ---- <Z_q>, <n_q> for ALL local qubits and <psi|psi> in one pass ---------------------------------
 // out partials per block: [0] = sum p_k, [1 + q] = sum p_k * bit_q(k)  (q = local bit position)
-__global__ void __launch_bounds__(256) marginals_kernel(const double2* __restrict__ psi, int nl, double* part) {
+// cond: only amplitudes with (k & cond) == cond contribute (cond = 1 << b gives the joint counts n_bq)
+__global__ void __launch_bounds__(256) marginals_kernel(const double2* __restrict__ psi, int nl, u64 cond, double* part) {
     __shared__ double red[32];
     const u64 dim = 1ull << nl;
     double tot = 0.0;
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(256) marginals_kernel(const double2* __restric
 #pragma unroll
     for (int q = 0; q < QSB_MAX_QUBITS_DEV; ++q) cnt[q] = 0.0;
     for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < dim; k += (u64)gridDim.x * blockDim.x) {
+        if ((k & cond) != cond) continue;
         const double pk = cnorm2(psi[k]);
         tot += pk;
 #pragma unroll

@@ -552,7 +552,7 @@ struct TermResult {
 
 // evaluate <psi|term_t|psi> (coef excluded) for a batch of Pauli terms into host results
 static int pauli_batch(qsb_ctx* c, int64_t n_terms, const u64* xm, const u64* ym, const u64* zm, const u64* nm,
-                       TermResult* out) {
+                       TermResult* out, const int* modes = nullptr) {
     const u64 lmask = c->dim - 1ull;
     const size_t cap = (c->slots_n - 2) / 2;
     const int grid = grid_for(c, c->dim, 256);
@@ -567,7 +567,8 @@ static int pauli_batch(qsb_ctx* c, int64_t n_terms, const u64* xm, const u64* ym
                 return fail(c, QSB_ERR_INVALID, "Pauli term %lld: masks overlap", (long long)(t0 + t));
             if ((x | y | z | nmk) >> c->n)
                 return fail(c, QSB_ERR_INVALID, "Pauli term %lld: mask beyond qubit count", (long long)(t0 + t));
-            const u64 flip = x | y, zz = y | z;
+            const int mode = modes ? modes[t0 + t] : 0;  // 1: weight 1 - sgn with sgn over the flipped bits
+            const u64 flip = x | y, zz = mode ? flip : (y | z);
             const u64 rank = (u64)c->rank;
             const u64 flip_g = flip >> c->nl, zz_g = zz >> c->nl, n_g = nmk >> c->nl;
             if ((rank & n_g) != n_g) continue;  // this shard has a 0 where N projects on 1
@@ -583,7 +584,7 @@ static int pauli_batch(qsb_ctx* c, int64_t n_terms, const u64* xm, const u64* ym
             a.flip = flip & lmask;
             a.zmask = zz & lmask;
             a.nmask = nmk & lmask;
-            a.mode = 0;
+            a.mode = mode;  // mode 1 is only used with shard-local masks (see qsb_sisj)
             a.nl = c->nl;
             a.part = c->part;
             sign[(size_t)t] = (__builtin_popcountll(rank & zz_g) & 1) ? -1.0 : 1.0;  // sharded Z / Y bits
@@ -622,11 +623,19 @@ static int pauli_batch(qsb_ctx* c, int64_t n_terms, const u64* xm, const u64* ym
 }
 
 // probabilities' marginals: tot = <psi|psi>, cnt[q] = <n_q> for global qubit q (whole register)
-static int marginals(qsb_ctx* c, double* tot, double* number /* n */) {
+// cond_qubit >= 0: restrict to basis states with that qubit excited -> tot = <n_c>, number[q] = <n_c n_q>
+static int marginals(qsb_ctx* c, double* tot, double* number /* n */, int cond_qubit = -1) {
     const int grid = std::min(grid_for(c, c->dim, 256), c->n_sm * 2);
     const int stride = c->nl + 1;
     if ((size_t)grid * stride > c->part_n) return fail(c, QSB_ERR_STATE, "partials buffer too small");
-    marginals_kernel<<<grid, 256, 0, c->stream>>>(c->psi, c->nl, c->part);
+    u64 cond = 0;
+    bool shard_in = true;  // a sharded condition qubit selects whole shards
+    if (cond_qubit >= 0) {
+        const int bit = c->n - 1 - cond_qubit;
+        if (bit < c->nl) cond = 1ull << bit;
+        else shard_in = ((c->rank >> (bit - c->nl)) & 1) != 0;
+    }
+    marginals_kernel<<<grid, 256, 0, c->stream>>>(c->psi, c->nl, cond, c->part);
     LAUNCHED(c);
     TRY(check_launch(c, "marginals_kernel"));
     finalize_rows_kernel<<<stride, 256, 0, c->stream>>>(c->part, grid, stride, c->slots);
@@ -635,6 +644,8 @@ static int marginals(qsb_ctx* c, double* tot, double* number /* n */) {
     TRY(fetch_slots(c, 0, (size_t)stride));
     // lay out per global qubit: qubit q <-> bit n-1-q; bits >= nl are rank bits
     std::vector<double> v(c->n + 1, 0.0);
+    if (!shard_in)
+        for (int i = 0; i <= c->nl; ++i) c->h_slots[i] = 0.0;
     v[0] = c->h_slots[0];
     for (int q = 0; q < c->n; ++q) {
         const int bit = c->n - 1 - q;
@@ -1157,28 +1168,46 @@ int qsb_sisj(qsb_ctx* c, double* out) {
     if (!c || !out) return fail(c, QSB_ERR_INVALID, "NULL argument");
     CU(cudaSetDevice(c->device));
     const int n = c->n;
-    const int np = n * (n - 1) / 2;
-    // per pair: ZZ (mode 0, zmask = m_i|m_j) and XX, YY (flip = m_i|m_j)
-    //   s_ij = <Z_iZ_j> + (1/3)(<X_iX_j> + <Y_iY_j>)       (qse/magnetic.py:213-243)
-    std::vector<u64> xm(3 * np, 0), ym(3 * np, 0), zm(3 * np, 0), nm(3 * np, 0);
-    int t = 0;
+    // s_ij = <Z_iZ_j> + (1/3)<X_iX_j + Y_iY_j>        (qse/magnetic.py:213-243)
+    // <Z_iZ_j> = <1> - 2<n_i> - 2<n_j> + 4<n_i n_j>: one conditional-marginal pass per qubit i gives
+    // <n_i n_j> for every j (N passes instead of N(N-1)/2).
+    double tot = 0.0;
+    std::vector<double> num(n), row(n), nij((size_t)n * n, 0.0);
+    TRY(marginals(c, &tot, num.data()));
+    for (int i = 0; i < n; ++i) {
+        double ni = 0.0;
+        TRY(marginals(c, &ni, row.data(), i));
+        for (int j = 0; j < n; ++j) nij[(size_t)i * n + j] = row[j];
+    }
+    // <XX + YY> = sum_k conj(psi[k^f]) (1 - z_i z_j) psi[k], f = m_i | m_j: ONE pass per pair when both
+    // qubits are shard-local (mode 1); pairs touching a sharded qubit take the XX and YY strings
+    // separately because their shard-dependent sign cannot be folded into the weight.
+    std::vector<u64> xm, ym, zm, nm;
+    std::vector<int> modes, pair_of;
+    int pidx = 0;
     for (int i = 0; i < n; ++i)
-        for (int j = i + 1; j < n; ++j, ++t) {
+        for (int j = i + 1; j < n; ++j, ++pidx) {
             const u64 m = (1ull << (n - 1 - i)) | (1ull << (n - 1 - j));
-            zm[t] = m;
-            xm[np + t] = m;
-            ym[2 * np + t] = m;
+            if ((m >> c->nl) == 0) {
+                xm.push_back(m); ym.push_back(0); zm.push_back(0); nm.push_back(0); modes.push_back(1); pair_of.push_back(pidx);
+            } else {
+                xm.push_back(m); ym.push_back(0); zm.push_back(0); nm.push_back(0); modes.push_back(0); pair_of.push_back(pidx);
+                xm.push_back(0); ym.push_back(m); zm.push_back(0); nm.push_back(0); modes.push_back(0); pair_of.push_back(pidx);
+            }
         }
-    std::vector<TermResult> res(3 * np, TermResult{0.0, 0.0});
+    std::vector<TermResult> res(xm.size(), TermResult{0.0, 0.0});
     TRY(rank_barrier(c));
-    TRY(pauli_batch(c, 3 * np, xm.data(), ym.data(), zm.data(), nm.data(), res.data()));
-    t = 0;
+    TRY(pauli_batch(c, (int64_t)xm.size(), xm.data(), ym.data(), zm.data(), nm.data(), res.data(), modes.data()));
+    std::vector<double> xxyy((size_t)n * (n - 1) / 2 + 1, 0.0);
+    for (size_t t = 0; t < res.size(); ++t) xxyy[pair_of[t]] += res[t].re;
+    pidx = 0;
     for (int i = 0; i < n; ++i) {
         out[(size_t)i * n + i] = 1.0;
-        for (int j = i + 1; j < n; ++j, ++t) {
-            const double s = res[t].re + (res[np + t].re + res[2 * np + t].re) / 3.0;
-            out[(size_t)i * n + j] = s;
-            out[(size_t)j * n + i] = s;
+        for (int j = i + 1; j < n; ++j, ++pidx) {
+            const double zz = tot - 2.0 * num[i] - 2.0 * num[j] + 4.0 * nij[(size_t)i * n + j];
+            const double sij = zz + xxyy[pidx] / 3.0;
+            out[(size_t)i * n + j] = sij;
+            out[(size_t)j * n + i] = sij;
         }
     }
     return QSB_OK;
