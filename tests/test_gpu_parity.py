@@ -544,3 +544,46 @@ def test_calculator_sample_final_state():
     top = max(counts, key=counts.get)
     assert int(top, 2) == int(np.argmax(p))
     calc.close()
+
+
+# ---- edge cases ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [3, 13])
+def test_edge_schedules(n):
+    reg = qb.lattices.random_register(n, 6.0, seed=n) if n > 1 else qb.Qbits(np.zeros((1, 2)))
+    v = orc.interaction_matrix(reg.positions)
+    e = orc.diagonal_energies(v, n)
+    psi = random_state(n, 77)
+    with lib.Engine(n) as eng:
+        eng.set_interaction(qb.interaction_matrix(reg.positions))
+        eng.set_state(psi)
+        # empty schedule and zero-length segments leave the state untouched (bit for bit)
+        assert eng.evolve_schedule(np.zeros(0), np.zeros(0), np.zeros(0)) is None
+        eng.evolve_schedule(np.array([3.0, 1.0]), np.array([1.0, -2.0]), np.zeros(2))
+        assert np.array_equal(eng.get_state(), psi)
+        # omega = 0: H is diagonal, the propagator is a pure phase per basis state
+        eng.evolve_schedule(np.array([0.0]), np.array([2.5]), np.array([0.003]))
+        diag = e - 2.5 * orc.popcounts(n)
+        assert np.max(np.abs(eng.get_state() - np.exp(-1j * diag * 0.003) * psi)) <= 1e-12
+        # e_ops given but empty: (steps, 0) expectations
+        out = eng.evolve_schedule(np.array([1.0, 1.0]), np.zeros(2), np.full(2, 0.001), lib.PackedEops([]))
+        assert out is None
+    # no interaction at all (far-apart atoms): product of single-qubit rotations
+    with lib.Engine(n) as eng:
+        eng.set_interaction(np.zeros((n, n)))
+        eng.evolve_schedule(np.array([4.0]), np.array([0.0]), np.array([0.1]))
+        one = orc.exact_single_qubit(4.0, 0.0, 0.1)
+        want = one
+        for _ in range(n - 1):
+            want = np.kron(want, one)
+        assert np.max(np.abs(eng.get_state() - want)) <= 1e-12
+
+
+def test_calculate_with_empty_e_ops_and_reuse():
+    qbits = qb.lattices.chain(0.9 * qb.blockade_radius(OMEGA_MAX), 3)
+    calc = qb.B200(qbits, qb.Signal([1.0, 2.0, 3.0], 30), qb.Signal([0.0, 0.5, 1.0], 30))
+    out = calc.calculate(e_ops=[])
+    assert out["expectations"].shape == (3, 0)
+    first = out["state"].copy()
+    again = calc.calculate()  # same schedule from |0...0> again: identical result, fresh dict
+    assert np.array_equal(again["state"], first) and again is not out
+    calc.close()
