@@ -268,7 +268,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                              "note": "fused Taylor step: same 40 B/amp currency, region time / number of H psi"}}
 
     if world > 1:
-        inbound = 16.0 * (1 << (n - p)) * p  # partner shards read over NVLink per H psi per GPU
+        # bytes pulled over NVLink per H psi per GPU: p partner shards (direct exchange, P = 2) or
+        # 2 * (P-1)/P of a shard (qubit-remap exchange, P >= 4)
+        inbound = 16.0 * (1 << (n - p)) * (p if world < 4 else 2.0 * (world - 1) / world)
         roofline["nvlink"] = {"bound": "nvlink", "achieved": inbound / t_hpsi / 1e9, "peak": 770.0, "unit": "GB/s",
                               "frac": inbound / t_hpsi / 1e9 / 770.0, "peak_source": "measured peer copy per direction "
                               "(B200_PROFILING.md); nominal 900", "bytes_per_hpsi_per_gpu": inbound,

@@ -83,7 +83,44 @@ struct HpsiWs {
     unsigned long long done_target;
     u64 n_tiles;     // tiles per sub-pass (= dim >> TB)
     int use_tmap;    // strided tiles are fetched with ONE 2-D tensor-map TMA per <= 256 rows
+    // remap exchange (P >= 4): zpeer[c] is rank c's Z buffer (remap_z_kernel); the sharded-qubit term of
+    // tile tau lives in chunk `rank` of the Z buffer of rank c = chunk index of tau -- ONE pull per tile
+    int remap;
+    int rank;
+    int cbits;       // log2 of the chunk (= shard / P)
+    const double2* zpeer[8];
 };
+
+// Qubit-remap exchange, step 1.  With P = 2^p ranks, view every shard as P chunks
+// (chunk index = top p LOCAL index bits).  This rank owns chunk column `rank`: it pulls chunk
+// `rank` of every rank's x ONCE (7/8 of a shard inbound at P = 8, instead of 3 full shards) and
+// forms, in registers, the hypercube-neighbour sums over the RANK index for all P of them:
+//     z[c][w] = sum_g x_{c ^ 2^g}[rank][w]
+// which is exactly the sharded-qubit term that rank c needs for its chunk `rank`; rank c pulls it
+// back inside the fused H psi launch (kItemPeer).  Inbound per amplitude: 2 * 16 * (P-1)/P bytes.
+struct RemapArgs {
+    const double2* xs[8];
+    double2* z;
+    int rank;
+    int cbits;
+};
+template <int P>
+__global__ void __launch_bounds__(256) remap_z_kernel(const RemapArgs a) {
+    const u64 clen = 1ull << a.cbits;
+    const u64 src0 = (u64)a.rank << a.cbits;
+    for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < clen; w += (u64)gridDim.x * blockDim.x) {
+        double2 v[P];
+#pragma unroll
+        for (int c = 0; c < P; ++c) v[c] = ldg2_volatile(a.xs[c] + src0 + w);
+#pragma unroll
+        for (int c = 0; c < P; ++c) {
+            double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int g = 1; g < P; g <<= 1) cacc(s, v[c ^ g]);
+            a.z[((u64)c << a.cbits) + w] = s;
+        }
+    }
+}
 
 QSB_DEV u64 ws_tile_base(int lb, int hb, int hb0, u64 tau) {
     const int mid_bits = hb0 - lb;
@@ -299,8 +336,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                     __syncwarp();
                     constexpr int kCopies = 4;
                     constexpr int chunk = C::kTileW / kCopies;
+                    const double2* psrc = p.peer[q] + pbase;
+                    if (p.remap) {
+                        const int tcb = p.cbits - TB;  // tiles per chunk (log2)
+                        psrc = p.zpeer[tau >> tcb] + ((u64)p.rank << p.cbits) + ((tau & ((1ull << tcb) - 1ull)) << TB);
+                    }
                     if (lane < kCopies)  // TMA pull from the partner's HBM over NVLink
-                        bulk_g2s(pstage + lane * chunk, p.peer[q] + pbase + (u64)lane * chunk, chunk * sizeof(double2), &full_bar[s]);
+                        bulk_g2s(pstage + lane * chunk, psrc + (u64)lane * chunk, chunk * sizeof(double2), &full_bar[s]);
                     if (lane == 0) {
                         desc[s].base = pbase;
                         desc[s].type = kItemPeer;

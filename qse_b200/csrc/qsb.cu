@@ -75,6 +75,9 @@ struct qsb_ctx {
     double2* peer_wa[64] = {nullptr};
     double2* peer_wb[64] = {nullptr};
     double2* stage[kMaxPeers] = {nullptr};  // NCCL-staged partner shards when IPC is unavailable
+    double2* zbuf = nullptr;                // remap exchange: neighbour sums in the transposed layout
+    double2* peer_z[64] = {nullptr};
+    int exchange = -1;                      // option "exchange": -1 auto, 0 direct partner pulls, 1 remap
     // measurement
     double* flush_buf = nullptr;
     size_t flush_n = 0;
@@ -246,11 +249,33 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, double omega
     const int grid = (int)std::min<u64>(n_tiles, (u64)c->n_sm);
     CU(cudaMemsetAsync(c->tickets, 0, 16 * sizeof(unsigned int), c->stream));
     HpsiWs a{};
+    // remap exchange: from 4 ranks up, when peer memory is mapped and a chunk holds whole tiles
+    const bool remap = c->nranks >= 4 && c->nranks <= 8 && c->ipc && c->zbuf && c->exchange != 0 && (c->nl - c->p) >= w.tb;
+    if (remap) {
+        RemapArgs ra{};
+        for (int r = 0; r < c->nranks; ++r) {
+            ra.xs[r] = peer_of(c, x, r);
+            if (!ra.xs[r]) return fail(c, QSB_ERR_STATE, "H psi input is not an exported buffer");
+            a.zpeer[r] = c->peer_z[r];
+        }
+        ra.z = c->zbuf;
+        ra.rank = c->rank;
+        ra.cbits = c->nl - c->p;
+        const int rgrid = grid_for(c, 1ull << ra.cbits, 256);
+        if (c->nranks == 4) remap_z_kernel<4><<<rgrid, 256, 0, c->stream>>>(ra);
+        else remap_z_kernel<8><<<rgrid, 256, 0, c->stream>>>(ra);
+        LAUNCHED(c);
+        TRY(check_launch(c, "remap_z_kernel"));
+        TRY(rank_barrier(c));  // every rank's Z must be complete before anyone pulls from it
+        a.remap = 1;
+        a.rank = c->rank;
+        a.cbits = ra.cbits;
+    }
     a.x = x;
     a.y = y;
     a.eint = c->eint;
     for (int g = 0; g < kMaxPeers; ++g) a.peer[g] = peers[g];
-    a.n_peer = c->p;
+    a.n_peer = remap ? 1 : c->p;
     a.half_omega = 0.5 * omega;
     a.delta = delta;
     a.scale = fuse ? scale : make_double2(1.0, 0.0);
@@ -690,14 +715,17 @@ static int setup_comm(qsb_ctx* c, const void* uid_bytes) {
     memcpy(&uid, uid_bytes, sizeof(uid));
     NC(api->CommInitRank(&c->comm, c->nranks, uid, c->rank));
 
-    // exchange IPC handles of the three state-sized buffers
+    // exchange IPC handles of the state-sized buffers (psi, wa, wb and, from 4 ranks up, the Z buffer
+    // of the remap exchange)
+    const int nbuf = c->nranks >= 4 ? 4 : 3;
+    if (nbuf == 4) CU(cudaMalloc(&c->zbuf, c->dim * sizeof(double2)));
     const size_t hsz = sizeof(cudaIpcMemHandle_t);
-    const size_t rec = 3 * hsz;
+    const size_t rec = (size_t)nbuf * hsz;
     std::vector<unsigned char> mine(rec), all(rec * c->nranks);
     bool ok = getenv("QSB_NO_IPC") == nullptr;
-    cudaIpcMemHandle_t h[3];
-    double2* bufs[3] = {c->psi, c->wa, c->wb};
-    for (int i = 0; i < 3 && ok; ++i) {
+    cudaIpcMemHandle_t h[4];
+    double2* bufs[4] = {c->psi, c->wa, c->wb, c->zbuf};
+    for (int i = 0; i < nbuf && ok; ++i) {
         if (cudaIpcGetMemHandle(&h[i], bufs[i]) != cudaSuccess) {
             ok = false;
             cudaGetLastError();
@@ -725,10 +753,11 @@ static int setup_comm(qsb_ctx* c, const void* uid_bytes) {
                 c->peer_psi[r] = c->psi;
                 c->peer_wa[r] = c->wa;
                 c->peer_wb[r] = c->wb;
+                c->peer_z[r] = c->zbuf;
                 continue;
             }
-            double2** dst[3] = {&c->peer_psi[r], &c->peer_wa[r], &c->peer_wb[r]};
-            for (int i = 0; i < 3; ++i) {
+            double2** dst[4] = {&c->peer_psi[r], &c->peer_wa[r], &c->peer_wb[r], &c->peer_z[r]};
+            for (int i = 0; i < nbuf; ++i) {
                 cudaIpcMemHandle_t hh;
                 memcpy(&hh, rec_all.data() + (rec + 8) * r + i * hsz, hsz);
                 void* ptr = nullptr;
@@ -881,10 +910,12 @@ int qsb_destroy(qsb_ctx* c) {
             if (c->peer_psi[r]) cudaIpcCloseMemHandle(c->peer_psi[r]);
             if (c->peer_wa[r]) cudaIpcCloseMemHandle(c->peer_wa[r]);
             if (c->peer_wb[r]) cudaIpcCloseMemHandle(c->peer_wb[r]);
+            if (c->peer_z[r]) cudaIpcCloseMemHandle(c->peer_z[r]);
         }
     }
     if (c->comm && nccl_api()->ok) nccl_api()->CommDestroy(c->comm);
     for (int g = 0; g < kMaxPeers; ++g) cudaFree(c->stage[g]);
+    cudaFree(c->zbuf);
     cudaFree(c->psi);
     cudaFree(c->wa);
     cudaFree(c->wb);
@@ -946,6 +977,9 @@ int qsb_set_option(qsb_ctx* c, const char* key, double value) {
         c->path = (int)value;
         c->force_flat = c->path == 1;
         c->plan = make_plan(c->nl, c->force_flat);
+    } else if (!strcmp(key, "exchange")) {
+        if (value != -1.0 && value != 0.0 && value != 1.0) return fail(c, QSB_ERR_INVALID, "exchange must be -1, 0 or 1");
+        c->exchange = (int)value;
     } else if (!strcmp(key, "small_kernel")) {
         c->small_kernel = value != 0.0;
     } else if (!strcmp(key, "tensor_map")) {

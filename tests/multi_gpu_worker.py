@@ -42,7 +42,7 @@ def main():
             os.environ["QSB_NO_IPC"] = "1"
         else:
             os.environ.pop("QSB_NO_IPC", None)
-        for n in (8, 14, 17):
+        for n in ((8, 14, 17, 19) if world >= 4 else (8, 14, 17)):
             reg = qb.lattices.random_register(n, 0.9 * qb.blockade_radius(omega_max), seed=n)
             plan = qdist.ShardPlan(n, world)
             v = orc.interaction_matrix(reg.positions)
@@ -61,6 +61,12 @@ def main():
             want = orc.apply_hamiltonian(psi, e, n, 3.1, -2.2)
             err = float(np.max(np.abs(y - want[sl])) / np.max(np.abs(want)))
             check(f"{exchange} n={n} H psi", err <= 1e-13, f"rel err {err:.2e}")
+            if exchange == "ipc" and world >= 4:
+                eng.set_option("exchange", 0)  # direct partner pulls instead of the remap exchange
+                y0 = eng.apply_h(3.1, -2.2)
+                err0 = float(np.max(np.abs(y0 - want[sl])) / np.max(np.abs(want)))
+                check(f"n={n} H psi, direct exchange", err0 <= 1e-13, f"rel err {err0:.2e}")
+                eng.set_option("exchange", -1)
             if exchange == "ipc":
                 spins = eng.spins()
                 d = float(np.max(np.abs(spins - orc.get_spins(psi, n))))

@@ -587,3 +587,23 @@ def test_calculate_with_empty_e_ops_and_reuse():
     again = calc.calculate()  # same schedule from |0...0> again: identical result, fresh dict
     assert np.array_equal(again["state"], first) and again is not out
     calc.close()
+
+
+def test_reference_notebook_workload():
+    """docs/use-cases/adiabatic.ipynb (ring of 8, Omega 0->2, delta -2->0, 1 ns values, e_ops H_i, H_f),
+    shortened to 400 values, through examples/adiabatic_ring.py against the exact propagator."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "adiabatic_ring.py")
+    spec = importlib.util.spec_from_file_location("adiabatic_ring", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    t = 400
+    out = mod.main(t)
+    qbits = qb.lattices.ring(qb.blockade_radius(1.0), 8)
+    e = orc.diagonal_energies(orc.interaction_matrix(qbits.positions), 8)
+    ref = orc.calculate(qbits.positions, [(np.linspace(0.0, 2.0, t), t)], [(np.linspace(-2.0, 0.0, t), t)], method="eigh",
+                        e_ops=[lambda s: orc.energy(s, e, 8, 0.0, -2.0), lambda s: orc.energy(s, e, 8, 2.0, 0.0)])
+    assert orc.infidelity(out["state"], ref["state"]) <= INFID_TOL
+    assert np.max(np.abs(out["expectations"] - ref["expectations"])) <= OBS_TOL
