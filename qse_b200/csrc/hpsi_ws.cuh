@@ -88,6 +88,8 @@ struct HpsiWs {
     int remap;
     int rank;
     int cbits;       // log2 of the chunk (= shard / P)
+    unsigned int sb_xor;  // remap: super-block order staggered per rank (rank r starts in chunk r) so that at any
+                     // moment the ranks pull from DIFFERENT sources instead of all hammering one GPU's links
     const double2* zpeer[8];
 };
 
@@ -313,6 +315,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                                 if (q & 1ull) { type = kItemInner; sb = q >> 1; }
                                 else { type = kItemFirst; sb = lag + (q >> 1); }
                             } else { type = kItemInner; sb = n_sb - lag + (ph - (2 * n_sb - lag)); }
+                            sb ^= (u64)p.sb_xor;
                             tau = sb * n_a + wi;
                         }
                     }

@@ -270,6 +270,7 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, double omega
         a.remap = 1;
         a.rank = c->rank;
         a.cbits = ra.cbits;
+        a.sb_xor = (ra.cbits >= w.sbits) ? ((unsigned int)c->rank << (ra.cbits - w.sbits)) : 0u;
     }
     a.x = x;
     a.y = y;
