@@ -62,7 +62,8 @@ def main():
             "step_ms": [float(x) for x in ms], "taylor_terms": met["last_terms"],
             "hpsi_ms": t_hpsi * 1e3, "hpsi_gbs_40B_aggregate": 40.0 * amps / t_hpsi / 1e9,
             "hpsi_frac_of_aggregate_hbm_peak": 40.0 * amps / t_hpsi / 1e9 / (6563.2 * world),
-            "nvlink_inbound_gbs_per_gpu": 16.0 * amps / world * p_ / t_hpsi / 1e9,
+            # qubit-remap exchange from 4 ranks up: 2 * (P-1)/P of a shard per H psi; else p full shards
+            "nvlink_inbound_gbs_per_gpu": 16.0 * amps / world * (p_ if world < 4 else 2.0 * (world - 1) / world) / t_hpsi / 1e9,
             "norm_after_sweep": norm, "max_rydberg_population": float(number.max()),
             "round_trip_infidelity": 1.0 - float(p[0]), "round_trip_argmax": int(idx[0]),
             "hpsi_launches": met["hpsi_passes"], "planned_hbm_bytes_per_amp": met["hpsi_bytes_per_amp"]}), flush=True)
