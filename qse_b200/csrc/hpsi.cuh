@@ -1,4 +1,7 @@
-// hpsi.cuh — matrix-free H psi for the Rydberg Hamiltonian (kernels K2/K3/K5 of SURVEY.md §2.2).
+// hpsi.cuh — matrix-free H psi for the Rydberg Hamiltonian (kernels K2/K3/K5 of SURVEY.md §2.2):
+// tile arithmetic shared with hpsi_ws.cuh, plus the round-1 v1 kernels that are kept as independent
+// cross-checks (qsb_set_option "hpsi_path" = 2 / 1) and for shards smaller than 2^13 amplitudes.
+// The production kernel is hpsi_ws_kernel (hpsi_ws.cuh).
 //
 //   y[k] = (E_int[k] - delta * popc(k)) x[k] + (omega/2) * sum_q x[k ^ (1 << q)]
 //

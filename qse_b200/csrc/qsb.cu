@@ -791,7 +791,8 @@ extern "C" {
 int qsb_abi_version(void) { return QSB_ABI_VERSION; }
 
 const char* qsb_build_info(void) {
-    return "libqsb sm_100a; tile 2^12 amplitudes, 512 threads, 2-stage bulk-copy pipeline; built " __DATE__;
+    return "libqsb sm_100a; warp-specialised H psi (TMA producer + 16 consumer warps, 2^12-amplitude tiles, "
+           "L2-resident super-blocks, tensor-map TMA); built " __DATE__;
 }
 
 int qsb_device_count(int* count) {
