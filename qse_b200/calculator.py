@@ -321,8 +321,43 @@ class B200(_Base):
                                 "or qse.Operator / qse.Operators with X/Y/Z/N strings")
         return lib.PackedEops(packed)
 
-    def calculate(self, e_ops=None):
-        """Time-evolve |0...0> through the pulse schedule (qse/calc/qutip.py:34-53)."""
+    # ---- checkpoint / resume (long sweeps at 30+ qubits; the reference has none: SURVEY.md section 5) ----
+    def save_checkpoint(self, prefix: str, next_step: int):
+        """Write this rank's shard of the current state to ``{prefix}.rank{r}.npy`` plus a JSON header.
+
+        ``next_step`` is the index of the first schedule value that has NOT been applied yet; pass the
+        same prefix to ``calculate(resume_from=prefix)`` to continue from there (same register, same
+        number of ranks).  SPMD: every rank calls it."""
+        import json
+
+        eng = self._engine_ready()
+        np.save(f"{prefix}.rank{eng.rank}.npy", eng.get_state())
+        if eng.rank == 0:
+            with open(f"{prefix}.json", "w") as fh:
+                json.dump({"format": "qse_b200-checkpoint-1", "nqbits": self._nqbits(), "nranks": eng.nranks,
+                           "next_step": int(next_step), "c6": float(self.c6),
+                           "positions": np.asarray(self.qbits.positions, dtype=float).tolist()}, fh)
+
+    def _load_checkpoint(self, prefix: str, eng) -> int:
+        import json
+
+        with open(f"{prefix}.json") as fh:
+            head = json.load(fh)
+        if head.get("format") != "qse_b200-checkpoint-1":
+            raise Exception(f"{prefix}.json is not a qse_b200 checkpoint")
+        if head["nqbits"] != self._nqbits() or head["nranks"] != eng.nranks:
+            raise Exception("checkpoint was written for a different register size or number of ranks")
+        if not np.array_equal(np.asarray(head["positions"], dtype=float), np.asarray(self.qbits.positions, dtype=float)):
+            raise Exception("checkpoint was written for different qubit positions")
+        eng.set_state(np.load(f"{prefix}.rank{eng.rank}.npy"))
+        return int(head["next_step"])
+
+    def calculate(self, e_ops=None, resume_from=None, stop_after=None):
+        """Time-evolve |0...0> through the pulse schedule (qse/calc/qutip.py:34-53).
+
+        ``resume_from`` (a ``save_checkpoint`` prefix) starts from the stored state at its
+        ``next_step`` instead; ``stop_after=k`` applies only the schedule values before index k (then
+        ``save_checkpoint(prefix, k)``).  Expectations are returned for the steps actually run."""
         if self.amplitude is None or self.detuning is None:
             raise Exception("The amplitude and detuning must be set before calculate().")
         _check_pulses(self.amplitude, self.detuning)
@@ -331,7 +366,15 @@ class B200(_Base):
         eng.set_option("tol", self.tol)
         eng.set_option("fixed_terms", 4 if self.method == "rk4" else 0)
         omega, delta, dt = flatten_schedule(self.amplitude, self.detuning)
-        eng.reset_state()
+        first = 0
+        if resume_from is not None:
+            first = self._load_checkpoint(resume_from, eng)
+        else:
+            eng.reset_state()
+        last = omega.size if stop_after is None else int(stop_after)
+        if not 0 <= first <= last <= omega.size:
+            raise Exception(f"cannot run schedule values [{first}, {last}) of {omega.size}")
+        omega, delta, dt = omega[first:last], delta[first:last], dt[first:last]
         before = eng.metrics()
         t1 = time.time()
         exps = eng.evolve_schedule(omega, delta, dt, self._pack_eops(e_ops) if e_ops is not None else None)

@@ -607,3 +607,28 @@ def test_reference_notebook_workload():
                         e_ops=[lambda s: orc.energy(s, e, 8, 0.0, -2.0), lambda s: orc.energy(s, e, 8, 2.0, 0.0)])
     assert orc.infidelity(out["state"], ref["state"]) <= INFID_TOL
     assert np.max(np.abs(out["expectations"] - ref["expectations"])) <= OBS_TOL
+
+
+def test_checkpoint_resume(tmp_path):
+    """A sweep interrupted after k values and resumed from the checkpoint equals the uninterrupted one."""
+    qbits = qb.lattices.triangular(0.9 * qb.blockade_radius(OMEGA_MAX), 3, 3)
+    amp, det = sweep(24, 2)
+    whole = qb.B200(qbits, amp, det)
+    ref = whole.calculate(e_ops=[whole.get_hamiltonian(OMEGA_MAX, 0.0)])
+    whole.close()
+    prefix = str(tmp_path / "ckpt")
+    part = qb.B200(qbits, amp, det)
+    head = part.calculate(e_ops=[part.get_hamiltonian(OMEGA_MAX, 0.0)], stop_after=10)
+    assert head["expectations"].shape == (10, 1)
+    part.save_checkpoint(prefix, next_step=10)
+    part.close()
+    resumed = qb.B200(qbits, amp, det)
+    tail = resumed.calculate(e_ops=[resumed.get_hamiltonian(OMEGA_MAX, 0.0)], resume_from=prefix)
+    assert tail["expectations"].shape == (14, 1)
+    assert np.max(np.abs(tail["state"] - ref["state"])) <= 1e-13
+    assert np.max(np.abs(np.vstack([head["expectations"], tail["expectations"]]) - ref["expectations"])) <= 1e-11
+    other = qb.B200(qb.lattices.chain(5.0, 9), amp, det)
+    with pytest.raises(Exception, match="different qubit positions"):
+        other.calculate(resume_from=prefix)
+    other.close()
+    resumed.close()
