@@ -249,7 +249,12 @@ class B200(_Base):
         """(rank, world, device) of this process."""
         rank, world = 0, 1
         use = self.distributed
-        if use is None or use:
+        import os
+        import sys
+
+        # importing torch costs seconds: only look for a process group when one can exist
+        maybe_distributed = "torch" in sys.modules or "WORLD_SIZE" in os.environ or "RANK" in os.environ
+        if use or (use is None and maybe_distributed):
             try:
                 import torch.distributed as dist
 
@@ -263,8 +268,6 @@ class B200(_Base):
             rank, world = 0, 1
         device = self.device
         if device is None:
-            import os
-
             device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else 0
         return rank, world, device
 
