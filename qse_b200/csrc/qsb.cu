@@ -193,7 +193,9 @@ static WsPlan make_ws_plan_tb(int nl, int sb_bits, int tb) {
 // Measured on B200 (tools/ab_hpsi.py): the super-block must leave at most 9 index bits to the
 // plain launch (else a third trip to HBM), 2^18 amplitudes (10 MiB of x+y+E) with a lead of 3 blocks
 // is best while that holds (N_local <= 27); larger blocks want a shorter lead to stay inside L2.
-static int auto_sb_bits(int nl) { return std::max(18, std::min(21, nl - 9)); }
+// Up to 21 local qubits the whole shard is ONE super-block (a single fused launch, measured faster:
+// 19/20/21 qubits 22/31/51 us against 28/39/63 us with a plain launch on top).
+static int auto_sb_bits(int nl) { return nl <= 21 ? nl : std::max(18, std::min(21, nl - 9)); }
 static int auto_sb_lag(int sbits) { return sbits <= 18 ? 3 : (sbits == 19 ? 2 : 1); }
 
 static WsPlan make_ws_plan(int nl, int sb_bits, int tile_bits) {

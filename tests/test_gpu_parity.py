@@ -90,7 +90,7 @@ def test_independent_kernels_agree(n):
             elif path == 1:
                 assert passes == 1
             else:
-                assert passes == (1 if n <= 18 else 2)
+                assert passes == (1 if n <= 21 else 2)
     assert np.max(np.abs(out[0] - out[1])) <= 1e-13 * np.max(np.abs(out[1]))
     assert np.max(np.abs(out[2] - out[1])) <= 1e-13 * np.max(np.abs(out[1]))
 
