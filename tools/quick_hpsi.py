@@ -32,7 +32,7 @@ for n in sizes:
             print(json.dumps({"n": n, "path": path, "sb": sb, "passes": eng.metrics()["hpsi_passes"], "hpsi_ms": round(float(np.median(ms)), 4),
                               "hpsi_gbs_40B": round(gbs, 1), "frac_measured_peak": round(gbs / PEAK, 4)}))
         eng.set_option("hpsi_path", 0)
-        eng.set_option("sb_bits", 19)
+        eng.set_option("sb_bits", 0)  # auto
         steps = 10
         om = np.linspace(1.0, 6.0, steps); de = np.linspace(-10, 10, steps); dt = np.full(steps, 0.001)
         ms = eng.time_schedule(om, de, dt)
