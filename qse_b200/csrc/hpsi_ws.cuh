@@ -1,16 +1,19 @@
-// hpsi_ws.cuh — warp-specialised H psi with L2-resident super-blocks (round-1 v2 of K2/K3).
+// hpsi_ws.cuh — warp-specialised H psi with L2-resident super-blocks: the production K2/K3 kernel.
 //
 // Same tile arithmetic as hpsi.cuh, different orchestration:
 //   * one producer warp per CTA takes work items from a global ticket counter, fills a 3-stage
-//     ring of 64 KiB tiles with TMA bulk copies (cp.async.bulk -> UBLKCP) and publishes each stage
-//     on a "full" mbarrier; 16 consumer warps process tiles and release stages through "empty"
-//     mbarriers.  No __syncthreads in the steady state: consumer warps drift apart, so the
-//     LDS-heavy flip phase of one warp overlaps the global loads/stores of another.
+//     ring of 64 KiB tiles through the TMA engine -- 1-D bulk copies (cp.async.bulk -> UBLKCP) for
+//     contiguous tiles, ONE 2-D tensor-map copy per <= 256 rows (cp.async.bulk.tensor.2d ->
+//     UTMALDG) for strided tiles -- issues L2 prefetches for the operands the consumers read with
+//     plain loads, and publishes each stage on a "full" mbarrier; 16 consumer warps process tiles
+//     and release stages through "empty" mbarriers.  No __syncthreads in the steady state.
+//   * sharded state: partner tiles (or, from 4 ranks up, tiles of the partners' remap buffers) are
+//     pulled over NVLink by the same producer with the same bulk copies (kItemPeer stages).
 //   * a FUSED launch covers the low `sbits` index bits in two sub-passes that share one trip to
 //     HBM: a super-block of 2^sbits amplitudes (x 16 B + y 16 B + E 8 B per amplitude) fits in the
 //     126 MB L2, so sub-pass B (index bits 12..sbits-1, strided rows) re-reads x and the partial
 //     y that sub-pass A (bits 0..11 + diagonal) just produced from L2.  Work items are ordered
-//     A(0) A(1) B(0) A(2) B(1) ... so that B(s) is handed out one whole phase after A(s); a B item
+//     A(0) .. A(L-1) A(L) B(0) A(L+1) B(1) ... so that B(s) is handed out L blocks after A(s); a B item
 //     still checks a per-super-block completion counter (release/acquire through L2) before its y
 //     is read.  A CTA only ever waits for tickets that were taken earlier by running CTAs, so the
 //     scheme cannot deadlock whatever the residency.
