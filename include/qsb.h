@@ -161,6 +161,12 @@ int qsb_topk_probs(qsb_ctx* ctx, int k, uint64_t* idx, double* prob);
  * results.sample_final_state (docs/tutorials/pulser-calc-example.ipynb cell 10). [collective] */
 int qsb_sample(qsb_ctx* ctx, uint64_t seed, int64_t shots, uint64_t* out);
 
+/* The launch plan of one H psi for a shard of 2^n_local amplitudes (host-only, needs no GPU):
+ * out[0] = tile bits, out[1] = super-block bits, out[2] = number of plain launches, then (lb, hb, hb0)
+ * of the inner sub-pass and of each plain launch: out[3 + 3*i ...].  out must hold 3 + 3*9 ints.
+ * sb_bits / tile_bits as in qsb_set_option (0 = auto). */
+int qsb_describe_plan(int n_local, int sb_bits, int tile_bits, int* out);
+
 /* ---- measurement ------------------------------------------------------------------- */
 typedef struct {
     uint64_t hpsi_calls;        /* H psi applications since creation */

@@ -1461,6 +1461,26 @@ int qsb_sample(qsb_ctx* c, uint64_t seed, int64_t shots, uint64_t* out) {
     return QSB_OK;
 }
 
+int qsb_describe_plan(int n_local, int sb_bits, int tile_bits, int* out) {
+    qsb_ctx* c = nullptr;
+    if (!out || n_local <= kTileBits || n_local >= QSB_MAX_QUBITS_DEV) return fail(c, QSB_ERR_INVALID, "n_local out of range");
+    if (sb_bits != 0 && (sb_bits < 13 || sb_bits > 21)) return fail(c, QSB_ERR_INVALID, "sb_bits must be 0 or in 13..21");
+    if (tile_bits != 0 && tile_bits != 11 && tile_bits != 12) return fail(c, QSB_ERR_INVALID, "tile_bits must be 0, 11 or 12");
+    const WsPlan w = make_ws_plan(n_local, sb_bits, tile_bits);
+    out[0] = w.tb;
+    out[1] = w.sbits;
+    out[2] = w.n_plain;
+    out[3] = w.inner.lb;
+    out[4] = w.inner.hb;
+    out[5] = w.inner.hb0;
+    for (int i = 0; i < w.n_plain; ++i) {
+        out[6 + 3 * i] = w.plain[i].lb;
+        out[7 + 3 * i] = w.plain[i].hb;
+        out[8 + 3 * i] = w.plain[i].hb0;
+    }
+    return QSB_OK;
+}
+
 int qsb_get_metrics(const qsb_ctx* c, qsb_metrics* out) {
     if (!c || !out) return fail(nullptr, QSB_ERR_INVALID, "NULL argument");
     *out = c->met;

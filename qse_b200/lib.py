@@ -80,6 +80,7 @@ SIGNATURES = {
     "qsb_probabilities": (C.c_int, [_ctx_p, _c_double_p]),
     "qsb_topk_probs": (C.c_int, [_ctx_p, C.c_int, _c_u64_p, _c_double_p]),
     "qsb_sample": (C.c_int, [_ctx_p, C.c_uint64, C.c_int64, _c_u64_p]),
+    "qsb_describe_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "qsb_get_metrics": (C.c_int, [_ctx_p, C.POINTER(QsbMetrics)]),
     "qsb_time_apply_h": (C.c_int, [_ctx_p, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "qsb_time_schedule": (C.c_int, [_ctx_p, _c_double_p, _c_double_p, _c_double_p, C.c_int64,
@@ -145,6 +146,17 @@ def nccl_unique_id() -> bytes:
     if rc != 0:
         raise QsbError(rc, load().qsb_last_error(None).decode())
     return buf.raw
+
+
+def describe_plan(n_local: int, sb_bits: int = 0, tile_bits: int = 12) -> dict:
+    """Launch plan of one H psi (host-only): tile / super-block bits and the (lb, hb, hb0) tile
+    geometry of the inner sub-pass and of every plain launch."""
+    out = (C.c_int * 32)()
+    rc = load().qsb_describe_plan(int(n_local), int(sb_bits), int(tile_bits), out)
+    if rc != 0:
+        raise QsbError(rc, load().qsb_last_error(None).decode())
+    geo = lambda i: {"lb": out[i], "hb": out[i + 1], "hb0": out[i + 2]}  # noqa: E731
+    return {"tile_bits": out[0], "sb_bits": out[1], "inner": geo(3), "plain": [geo(6 + 3 * i) for i in range(out[2])]}
 
 
 def pinned_empty(n: int, dtype=np.complex128) -> np.ndarray:

@@ -98,3 +98,25 @@ def test_sharded_algorithm_reproduces_full_hpsi():
         for g in plan.sharded_qubits():
             y = y + 0.5 * omega * psi[plan.shard_slice(plan.partner(r, g))]
         assert np.max(np.abs(y - full[sl])) < 1e-12
+
+
+@pytest.mark.parametrize("tile_bits", [12, 11])
+@pytest.mark.parametrize("sb_bits", [0, 13, 18, 21])
+def test_hpsi_launch_plan_covers_every_qubit_once(tile_bits, sb_bits):
+    """The planner of the H psi launches (host-only entry point, no GPU): over all sub-passes every
+    local index bit is an ACTIVE tile bit exactly once, tiles hold 2^tile_bits amplitudes, rows are
+    at least 128 bytes, and at most two launches touch HBM up to 30 local qubits (auto plan)."""
+    from qse_b200 import lib
+
+    for nl in range(13, 34):
+        plan = lib.describe_plan(nl, sb_bits, tile_bits)
+        tb, sb = plan["tile_bits"], plan["sb_bits"]
+        assert tb == tile_bits and tb < sb <= min(nl, 21)
+        active = list(range(tb))  # FIRST sub-pass: the contiguous tile
+        for geo in [plan["inner"]] + plan["plain"]:
+            assert geo["lb"] + geo["hb"] == tb and geo["lb"] >= 3 and geo["hb"] >= 1  # >= 128-byte rows
+            active += list(range(geo["hb0"], geo["hb0"] + geo["hb"]))
+        assert sorted(active) == list(range(nl)), (nl, plan)
+        assert plan["inner"]["hb0"] == tb and plan["inner"]["hb"] == sb - tb
+        if sb_bits == 0 and tile_bits == 12:
+            assert len(plan["plain"]) == (0 if nl <= 21 else 1 if nl <= 30 else 2)
