@@ -166,6 +166,11 @@ int qsb_sample(qsb_ctx* ctx, uint64_t seed, int64_t shots, uint64_t* out);
  * of the inner sub-pass and of each plain launch: out[3 + 3*i ...].  out must hold 3 + 3*9 ints.
  * sb_bits / tile_bits as in qsb_set_option (0 = auto). */
 int qsb_describe_plan(int n_local, int sb_bits, int tile_bits, int* out);
+/* The static work schedule of the fused launch (host-only): ticket -> *type (0 = first sub-pass,
+ * 1 = inner sub-pass) and *tile, for n_sb super-blocks of n_a tiles, a lead of `lag` super-blocks and
+ * the per-rank order permutation sb_xor.  The function the kernel's producer warp evaluates. */
+int qsb_describe_ticket(uint64_t ticket, uint64_t n_a, uint64_t n_sb, uint64_t lag, uint64_t sb_xor,
+                        int* type, uint64_t* tile);
 
 /* ---- measurement ------------------------------------------------------------------- */
 typedef struct {

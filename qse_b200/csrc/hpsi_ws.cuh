@@ -127,6 +127,36 @@ __global__ void __launch_bounds__(256) remap_z_kernel(const RemapArgs a) {
     }
 }
 
+// Static schedule of the fused launch: ticket -> (item type, tile index).  Tickets enumerate phases
+// of n_a tiles:  A(0) .. A(L-1),  then  A(s), B(s-L)  for s = L .. n_sb-1,  then  B(n_sb-L) .. B(n_sb-1)
+// (A = FIRST tiles of super-block s, B = its INNER tiles, L = lag).  sb_xor permutes the super-block
+// order (remap exchange: every rank starts in a different chunk).  Host-callable so that the CPU
+// tests can check the invariants the kernel relies on (tests/test_host_logic.py).
+__host__ __device__ inline int ws_decode_ticket(u64 ticket, u64 n_a, u64 n_sb, u64 lag, u64 sb_xor, u64* tau) {
+    const u64 ph = ticket / n_a, wi = ticket % n_a;
+    int type;
+    u64 sb;
+    if (ph < lag) {
+        type = 0;  // kItemFirst
+        sb = ph;
+    } else if (ph < 2 * n_sb - lag) {
+        const u64 q = ph - lag;
+        if (q & 1ull) {
+            type = 1;  // kItemInner
+            sb = q >> 1;
+        } else {
+            type = 0;
+            sb = lag + (q >> 1);
+        }
+    } else {
+        type = 1;
+        sb = n_sb - lag + (ph - (2 * n_sb - lag));
+    }
+    sb ^= sb_xor;
+    *tau = sb * n_a + wi;
+    return type;
+}
+
 QSB_DEV u64 ws_tile_base(int lb, int hb, int hb0, u64 tau) {
     const int mid_bits = hb0 - lb;
     const u64 mid = tau & ((1ull << mid_bits) - 1ull);
@@ -310,16 +340,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                             type = kItemPlain;
                             tau = ticket;
                         } else {
-                            const u64 ph = ticket / n_a, wi = ticket % n_a;
-                            u64 sb;
-                            if (ph < lag) { type = kItemFirst; sb = ph; }
-                            else if (ph < 2 * n_sb - lag) {
-                                const u64 q = ph - lag;
-                                if (q & 1ull) { type = kItemInner; sb = q >> 1; }
-                                else { type = kItemFirst; sb = lag + (q >> 1); }
-                            } else { type = kItemInner; sb = n_sb - lag + (ph - (2 * n_sb - lag)); }
-                            sb ^= (u64)p.sb_xor;
-                            tau = sb * n_a + wi;
+                            type = ws_decode_ticket(ticket, n_a, n_sb, lag, (u64)p.sb_xor, &tau);
                         }
                     }
                 }

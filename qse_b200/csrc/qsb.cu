@@ -1481,6 +1481,17 @@ int qsb_describe_plan(int n_local, int sb_bits, int tile_bits, int* out) {
     return QSB_OK;
 }
 
+int qsb_describe_ticket(uint64_t ticket, uint64_t n_a, uint64_t n_sb, uint64_t lag, uint64_t sb_xor, int* type,
+                        uint64_t* tile) {
+    qsb_ctx* c = nullptr;
+    if (!type || !tile || n_a == 0 || n_sb == 0 || lag == 0 || lag > n_sb || ticket >= 2 * n_a * n_sb || sb_xor >= n_sb)
+        return fail(c, QSB_ERR_INVALID, "bad schedule parameters");
+    u64 tau = 0;
+    *type = ws_decode_ticket(ticket, n_a, n_sb, lag, sb_xor, &tau);
+    *tile = tau;
+    return QSB_OK;
+}
+
 int qsb_get_metrics(const qsb_ctx* c, qsb_metrics* out) {
     if (!c || !out) return fail(nullptr, QSB_ERR_INVALID, "NULL argument");
     *out = c->met;

@@ -81,6 +81,8 @@ SIGNATURES = {
     "qsb_topk_probs": (C.c_int, [_ctx_p, C.c_int, _c_u64_p, _c_double_p]),
     "qsb_sample": (C.c_int, [_ctx_p, C.c_uint64, C.c_int64, _c_u64_p]),
     "qsb_describe_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "qsb_describe_ticket": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_int),
+                                       _c_u64_p]),
     "qsb_get_metrics": (C.c_int, [_ctx_p, C.POINTER(QsbMetrics)]),
     "qsb_time_apply_h": (C.c_int, [_ctx_p, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "qsb_time_schedule": (C.c_int, [_ctx_p, _c_double_p, _c_double_p, _c_double_p, C.c_int64,

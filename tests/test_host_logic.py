@@ -120,3 +120,34 @@ def test_hpsi_launch_plan_covers_every_qubit_once(tile_bits, sb_bits):
         assert plan["inner"]["hb0"] == tb and plan["inner"]["hb"] == sb - tb
         if sb_bits == 0 and tile_bits == 12:
             assert len(plan["plain"]) == (0 if nl <= 21 else 1 if nl <= 30 else 2)
+
+
+@pytest.mark.parametrize("n_sb,n_a,lag,sb_xor", [(1, 4, 1, 0), (2, 8, 1, 0), (8, 4, 3, 0), (8, 4, 8, 5), (16, 2, 2, 12), (32, 1, 3, 7)])
+def test_fused_launch_schedule_invariants(n_sb, n_a, lag, sb_xor):
+    """The ticket order the producer warps follow (evaluated on the host through the C ABI): every
+    (sub-pass, tile) is handed out exactly once, and every INNER tile of a super-block comes after ALL
+    FIRST tiles of that block, by at least lag - 1 whole phases — what makes the in-kernel dependency
+    wait deadlock-free (a CTA only waits for earlier tickets) and short."""
+    import ctypes
+
+    from qse_b200 import lib
+
+    dll = lib.load()
+    seen, last_first, first_inner = set(), {}, {}
+    kind, tile = ctypes.c_int(), ctypes.c_uint64()
+    for ticket in range(2 * n_a * n_sb):
+        assert dll.qsb_describe_ticket(ticket, n_a, n_sb, lag, sb_xor, ctypes.byref(kind), ctypes.byref(tile)) == 0
+        key = (kind.value, tile.value)
+        assert key not in seen and 0 <= tile.value < n_a * n_sb and kind.value in (0, 1)
+        seen.add(key)
+        sb = tile.value // n_a
+        if kind.value == 0:
+            last_first[sb] = ticket
+        else:
+            first_inner.setdefault(sb, ticket)
+    assert len(seen) == 2 * n_a * n_sb
+    for sb in range(n_sb):
+        assert first_inner[sb] > last_first[sb]
+        gap = first_inner[sb] - last_first[sb] - 1
+        assert gap >= (min(lag, n_sb) - 1) * n_a - (n_a if sb >= n_sb - lag else 0) or n_sb <= lag
+    assert dll.qsb_describe_ticket(2 * n_a * n_sb, n_a, n_sb, lag, sb_xor, ctypes.byref(kind), ctypes.byref(tile)) == -1
