@@ -180,7 +180,7 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -324,12 +324,26 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         line["cpu_baseline"] = {"value": gbs, "unit": "GB/s", "cores": info["cores"], "kind": "port",
                                 "sample": info["sample"], "steps_per_s": sps}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) to stderr."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)  # libraries that write to fd 1 (NCCL's version banner) now land on stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
