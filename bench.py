@@ -167,7 +167,7 @@ def cpu_port_run(n_qubits: int, steps: int, warmup: int, budget_s: float):
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
-    n = 25 + (world.bit_length() - 1)
+    n = args.qubits + (world.bit_length() - 1)
     gbs, sps, info = cpu_port_run(n, args.steps, args.warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": "hpsi_hbm_gbs_in_sweep", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
