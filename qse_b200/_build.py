@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libqsb.so")
 SOURCES = [os.path.join(CSRC, "qsb.cu")]
-HEADERS = [os.path.join(CSRC, f) for f in ("common.cuh", "hpsi.cuh", "hpsi_ws.cuh", "small.cuh", "observe.cuh", "nccl_dl.h")] + [
+HEADERS = [os.path.join(CSRC, f) for f in ("common.cuh", "hpsi.cuh", "hpsi_ws.cuh", "small.cuh", "observe.cuh", "terms.cuh", "nccl_dl.h")] + [
     os.path.join(os.path.dirname(HERE), "include", "qsb.h")
 ]
 NVCC_FLAGS = [

@@ -128,6 +128,11 @@ QSB_DEV unsigned long long ld_volatile_u64(const unsigned long long* p) {
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+QSB_DEV double ld_volatile_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
 QSB_DEV unsigned int ld_volatile_u32(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

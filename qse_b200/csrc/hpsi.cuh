@@ -3,10 +3,12 @@
 // cross-checks (qsb_set_option "hpsi_path" = 2 / 1) and for shards smaller than 2^13 amplitudes.
 // The production kernel is hpsi_ws_kernel (hpsi_ws.cuh).
 //
-//   y[k] = (E_int[k] - delta * popc(k)) x[k] + (omega/2) * sum_q x[k ^ (1 << q)]
+//   y[k] = (E[k] - sum_q delta_q b_q(k)) x[k] + sum_q hw_q x[k ^ (1 << q)]        (hw_q = Omega_q / 2)
 //
 // which is `get_hamiltonian(amp, det) * state` of the reference (qse/calc/qutip.py:43-44, 55-58):
-// the CSR mat-vec QuTiP performs ~10-30 times per sesolve call.  No matrix is ever formed.
+// the CSR mat-vec QuTiP performs ~10-30 times per sesolve call -- with the per-site drive and
+// detuning of README.md:93-95 (the global pulse is hw_q = Omega/2, delta_q = delta for every q).
+// No matrix is ever formed.
 //
 // The sum over qubits is a hypercube stencil: amplitude k needs N partners at distances 2^q.
 // A "tile" is 2^12 amplitudes held in shared memory; the bits of the basis index a tile spans
@@ -38,6 +40,25 @@ constexpr int kRegBits = 3;                   // log2(kPerThread)
 constexpr int kSmemBits = kTileBits - kRegBits;  // tile bits 0..8 go through shared memory
 constexpr int kStages = 2;
 constexpr int kMaxPeers = 3;
+constexpr int kMaxLocalBits = 34;
+
+// Per-site coefficients of one H(t), indexed by LOCAL index bit b (qubit n-1-b) / rank bit g.
+struct SiteParams {
+    double hw[kMaxLocalBits];   // Omega_q / 2 (+ static X coefficient) of the qubit at index bit b
+    double dl[kMaxLocalBits];   // delta_q of the qubit at index bit b
+    double d_rank;              // sum of delta_q over this rank's set sharded bits
+    double hw_peer[kMaxPeers];  // Omega_q / 2 of the sharded qubit behind rank bit g
+};
+// what the LAST pass adds to the accumulator (Taylor epilogue) and what it reduces
+enum { kAccNone = 0, kAccTerm = 1, kAccPair = 2 };  // acc += out  /  acc += x + out (two terms per RMW)
+enum { kRedNorm = 0, kRedDot = 1 };                 // |out|^2  /  Re conj(x) out
+
+// sum_q delta_q b_q(k) over the local index bits of k (generic form: one add per set bit)
+QSB_DEV double site_detuning(const SiteParams& sp, u64 k) {
+    double d = sp.d_rank;
+    for (u64 rest = k; rest; rest &= rest - 1ull) d += sp.dl[__ffsll((long long)rest) - 1];
+    return d;
+}
 constexpr size_t kTileSmemBytes = (size_t)kStages * kTile * sizeof(double2);
 
 struct HpsiPass {
@@ -48,14 +69,13 @@ struct HpsiPass {
     double* norm_part;     // LAST only, may be null: per-CTA sum of |out|^2
     const double2* peer[kMaxPeers];  // FIRST only: x of the partner rank for each sharded qubit
     int n_peer;
-    double half_omega;
-    double delta;
+    SiteParams sp;
     double2 scale;  // LAST: out = scale * (H x)
+    int acc_mode, red_mode;  // LAST: kAcc*, kRed*
     int nl;         // local qubits
     int lb;         // contiguous low tile bits
     int hb;         // high tile bits
     int hb0;        // position of the first high tile bit
-    int pop_rank;   // popcount of this rank's sharded-qubit bits
     u64 n_tiles;
 };
 
@@ -134,6 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) hpsi_tile_kernel(const HpsiPass p
         mbar_wait(&full_bar[s], parity);
 
         double2 xv[kPerThread], sum[kPerThread];
+        const int gshift = FIRST ? 0 : (p.hb0 - p.lb);  // tile bit b >= lb is index bit b + gshift
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) xv[j] = ts[t + j * kThreads];
         // flips of tile bits 9..11: partners are this thread's own registers
@@ -142,49 +163,58 @@ __global__ void __launch_bounds__(kThreads, 1) hpsi_tile_kernel(const HpsiPass p
             double2 a = make_double2(0.0, 0.0);
 #pragma unroll
             for (int b = 0; b < kRegBits; ++b)
-                if (kSmemBits + b >= act_lo) cacc(a, xv[j ^ (1 << b)]);
+                if (kSmemBits + b >= act_lo) {
+                    const double h = p.sp.hw[kSmemBits + b + gshift];
+                    a.x = fma(h, xv[j ^ (1 << b)].x, a.x);
+                    a.y = fma(h, xv[j ^ (1 << b)].y, a.y);
+                }
             sum[j] = a;
         }
         double2 accv[kPerThread];
-        if (LAST && p.acc != nullptr) {
+        if (LAST && p.acc_mode != kAccNone) {
 #pragma unroll
             for (int j = 0; j < kPerThread; ++j) accv[j] = p.acc[g[j]];
         }
         // flips of tile bits act_lo..8: XOR-permuted shared-memory reads
-        if (FIRST) {
+        for (int b = act_lo; b < kSmemBits; ++b) {
+            const int tb = t ^ (1 << b);
+            const double h = p.sp.hw[b + gshift];
 #pragma unroll
-            for (int b = 0; b < kSmemBits; ++b) {
-                const int tb = t ^ (1 << b);
-#pragma unroll
-                for (int j = 0; j < kPerThread; ++j) cacc(sum[j], ts[tb + j * kThreads]);
-            }
-        } else {
-            for (int b = act_lo; b < kSmemBits; ++b) {
-                const int tb = t ^ (1 << b);
-#pragma unroll
-                for (int j = 0; j < kPerThread; ++j) cacc(sum[j], ts[tb + j * kThreads]);
+            for (int j = 0; j < kPerThread; ++j) {
+                const double2 q = ts[tb + j * kThreads];
+                sum[j].x = fma(h, q.x, sum[j].x);
+                sum[j].y = fma(h, q.y, sum[j].y);
             }
         }
         if (FIRST) {
             for (int q = 0; q < p.n_peer; ++q) {
                 const double2* __restrict__ px = p.peer[q];
+                const double h = p.sp.hw_peer[q];
 #pragma unroll
-                for (int j = 0; j < kPerThread; ++j) cacc(sum[j], px[g[j]]);
+                for (int j = 0; j < kPerThread; ++j) {
+                    const double2 w = px[g[j]];
+                    sum[j].x = fma(h, w.x, sum[j].x);
+                    sum[j].y = fma(h, w.y, sum[j].y);
+                }
             }
         }
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) {
             double2 v;
             if (FIRST) {
-                const double d = e[j] - p.delta * (double)(__popcll(g[j]) + p.pop_rank);
-                v = make_double2(d * xv[j].x + p.half_omega * sum[j].x, d * xv[j].y + p.half_omega * sum[j].y);
+                const double d = e[j] - site_detuning(p.sp, g[j]);
+                v = make_double2(fma(d, xv[j].x, sum[j].x), fma(d, xv[j].y, sum[j].y));
             } else {
-                v = make_double2(yv[j].x + p.half_omega * sum[j].x, yv[j].y + p.half_omega * sum[j].y);
+                v = cadd(yv[j], sum[j]);
             }
             if (LAST) {
                 v = cmul(p.scale, v);
-                nrm += cnorm2(v);
-                if (p.acc != nullptr) p.acc[g[j]] = cadd(accv[j], v);
+                nrm += (p.red_mode == kRedDot) ? (xv[j].x * v.x + xv[j].y * v.y) : cnorm2(v);
+                if (p.acc_mode != kAccNone) {
+                    double2 a = cadd(accv[j], v);
+                    if (p.acc_mode == kAccPair) cacc(a, xv[j]);
+                    p.acc[g[j]] = a;
+                }
             }
             p.y[g[j]] = v;
         }
@@ -211,11 +241,11 @@ struct HpsiFlat {
     double* norm_part;
     const double2* peer[kMaxPeers];
     int n_peer;
-    double half_omega, delta;
+    SiteParams sp;
     double2 scale;
     int nl;
-    int pop_rank;
-    int fuse;  // apply scale / acc / norm
+    int fuse;  // apply scale / acc / reduction
+    int acc_mode, red_mode;
 };
 
 __global__ void __launch_bounds__(256) hpsi_flat_kernel(const HpsiFlat p) {
@@ -224,15 +254,26 @@ __global__ void __launch_bounds__(256) hpsi_flat_kernel(const HpsiFlat p) {
     double nrm = 0.0;
     for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < dim; k += (u64)gridDim.x * blockDim.x) {
         const double2 xk = p.x[k];
-        double2 s = make_double2(0.0, 0.0);
-        for (int q = 0; q < p.nl; ++q) cacc(s, p.x[k ^ (1ull << q)]);
-        for (int q = 0; q < p.n_peer; ++q) cacc(s, p.peer[q][k]);
-        const double d = p.eint[k] - p.delta * (double)(__popcll(k) + p.pop_rank);
-        double2 v = make_double2(d * xk.x + p.half_omega * s.x, d * xk.y + p.half_omega * s.y);
+        const double d = p.eint[k] - site_detuning(p.sp, k);
+        double2 v = make_double2(d * xk.x, d * xk.y);
+        for (int q = 0; q < p.nl; ++q) {
+            const double2 w = p.x[k ^ (1ull << q)];
+            v.x = fma(p.sp.hw[q], w.x, v.x);
+            v.y = fma(p.sp.hw[q], w.y, v.y);
+        }
+        for (int q = 0; q < p.n_peer; ++q) {
+            const double2 w = p.peer[q][k];
+            v.x = fma(p.sp.hw_peer[q], w.x, v.x);
+            v.y = fma(p.sp.hw_peer[q], w.y, v.y);
+        }
         if (p.fuse) {
             v = cmul(p.scale, v);
-            nrm += cnorm2(v);
-            if (p.acc != nullptr) p.acc[k] = cadd(p.acc[k], v);
+            nrm += (p.red_mode == kRedDot) ? (xk.x * v.x + xk.y * v.y) : cnorm2(v);
+            if (p.acc_mode != kAccNone) {
+                double2 a = cadd(p.acc[k], v);
+                if (p.acc_mode == kAccPair) cacc(a, xk);
+                p.acc[k] = a;
+            }
         }
         p.y[k] = v;
     }

@@ -1,5 +1,11 @@
 // hpsi_ws.cuh — warp-specialised H psi with L2-resident super-blocks: the production K2/K3 kernel.
 //
+//   y[k] = (E[k] - sum_q delta_q b_q(k)) x[k] + sum_q hw_q x[k ^ (1 << q)]          (hw_q = Omega_q / 2)
+//
+// i.e. `get_hamiltonian(amp, det) * state` of the reference (qse/calc/qutip.py:43-44, 55-58) with the
+// per-site drive and detuning of the reference's headline Hamiltonian (README.md:93-95); the global
+// pulse of qse.calc.Qutip is the special case hw_q = Omega/2, delta_q = delta for every site.
+//
 // Same tile arithmetic as hpsi.cuh, different orchestration:
 //   * one producer warp per CTA takes work items from a global ticket counter, fills a 3-stage
 //     ring of 64 KiB tiles through the TMA engine -- 1-D bulk copies (cp.async.bulk -> UBLKCP) for
@@ -18,9 +24,18 @@
 //     is read.  A CTA only ever waits for tickets that were taken earlier by running CTAs, so the
 //     scheme cannot deadlock whatever the residency.
 //   * the remaining high bits (>= sbits) are handled by PLAIN launches of the same kernel
-//     (strided-row tiles, no dependencies), the last of which applies the fused Taylor epilogue.
+//     (strided-row tiles, no dependencies), the last of which applies the fused Taylor epilogue
+//     (scale, accumulate -- one term or a PAIR of terms per read-modify-write of psi --, |term|^2 or
+//     Re<x|Hx>), and whose last CTA reduces the per-CTA partials in a fixed order: no finalize
+//     kernel, no memset, no host round trip per term.
 // HBM traffic per amplitude: 40 B for the fused launch + 48 B per plain launch (25 qubits: 88 B
 // instead of 136 B with one launch per tile-bit group).
+//
+// Arithmetic: every flip is ONE fused multiply-add per component, v = fma(hw_q, x[k ^ m_q], v), the
+// coefficient coming straight from the constant bank -- a per-site drive costs exactly what the
+// global one does.  The accumulators (8 amplitudes = 32 registers) are the only state a thread
+// carries through the shared-memory flip phase, which leaves room for eight 16-byte loads in
+// flight per thread and no spills (round 1 carried sum + x + y = 96 registers and spilled y).
 #pragma once
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
@@ -32,17 +47,14 @@ namespace qsb {
 constexpr int kConsumerWarps = 16;
 // warps 0..15 consume, warp 16 produces, warps 17..19 only pad the producer to a full warpgroup:
 // registers are allocated per warpgroup, and setmaxnreg moves the producer group's share
-// (96 -> 32 per thread) to the consumers (96 -> 112).
+// (96 -> 40 per thread) to the consumers (96 -> 112).
 constexpr int kWsThreads = (kConsumerWarps + 4) * 32;  // 640
 constexpr size_t kWsSmemBytes = 192 * 1024;            // the tile ring
 
 // Tile geometry.  A tile holds 2^TB amplitudes; a consumer thread owns 8 of them, so a tile is
 // processed by a GROUP of 2^(TB-3) threads and the 16 consumer warps form 16*32 / 2^(TB-3)
 // independent groups (group g takes work items g, g + kGroups, ...).  TB = 12: one group, 3 stages
-// of 64 KiB.  TB = 11: two groups, 6 stages of 32 KiB -- same total shared-memory work per H psi
-// (19 LDS.128 per amplitude at 25 qubits either way) but two tiles in flight per group, which is
-// what hides the 3-5 us it takes the TMA engine to land a tile, and two groups that drift out of
-// phase so that the flip phase of one overlaps the global loads/stores of the other.
+// of 64 KiB.  TB = 11: two groups, 6 stages of 32 KiB.
 template <int TB>
 struct WsCfg {
     static constexpr int kTileBitsW = TB;
@@ -60,6 +72,7 @@ enum { kItemFirst = 0, kItemInner = 1, kItemPlain = 2, kItemDone = 3, kItemPeer 
 
 struct WsItem {
     u64 base;
+    double dhi;  // FIRST: sum of delta_q over the set index bits >= TB of the tile base (+ the rank's bits)
     int type;
     int sb;
 };
@@ -72,20 +85,26 @@ struct HpsiWs {
     double* norm_part;
     const double2* peer[kMaxPeers];
     int n_peer;
-    double half_omega, delta;
+    SiteParams sp;   // per-site Omega_q / 2 and delta_q by index bit (hw_peer = 1.0 with the remap exchange)
     double2 scale;
     int nl;
-    int pop_rank;
     int fused;       // 1: fused FIRST+INNER launch over super-blocks; 0: plain launch
     int sbits;       // fused: log2 of the super-block
     int lb, hb, hb0; // geometry of the strided tiles (inner sub-pass or plain pass): lb + hb = TB
-    int last;        // the strided tiles of this launch finish H psi (apply scale / acc / norm)
+    int last;        // the strided tiles of this launch finish H psi (apply scale / acc / reduction)
+    int acc_mode;    // kAccNone / kAccTerm (acc += out) / kAccPair (acc += x + out)
+    int red_mode;    // kRedNorm / kRedDot
     int lag;         // fused: lead of the FIRST tiles over the INNER tiles, in super-blocks
     unsigned int* ticket;
+    unsigned int ticket_base;   // the counter is never reset: tickets of this launch start here
+    unsigned int* tail;         // last launch: CTAs that have stored their partial (reset by the last one)
+    double* red_out;            // last launch: sum of the per-CTA partials, fixed order
     unsigned long long* done;   // per super-block: FIRST tiles completed (cumulative over launches)
     unsigned long long done_target;
     u64 n_tiles;     // tiles per sub-pass (= dim >> TB)
     int use_tmap;    // strided tiles are fetched with ONE 2-D tensor-map TMA per <= 256 rows
+    u64 zero;        // always 0, but only the host knows: (bits & zero) makes an address DEPEND on a value, which
+                     // pins a load after the phase that produced the value whatever ptxas would like to hoist
     // remap exchange (P >= 4): zpeer[c] is rank c's Z buffer (remap_z_kernel); the sharded-qubit term of
     // tile tau lives in chunk `rank` of the Z buffer of rank c = chunk index of tau -- ONE pull per tile
     int remap;
@@ -100,12 +119,13 @@ struct HpsiWs {
 // (chunk index = top p LOCAL index bits).  This rank owns chunk column `rank`: it pulls chunk
 // `rank` of every rank's x ONCE (7/8 of a shard inbound at P = 8, instead of 3 full shards) and
 // forms, in registers, the hypercube-neighbour sums over the RANK index for all P of them:
-//     z[c][w] = sum_g x_{c ^ 2^g}[rank][w]
+//     z[c][w] = sum_g hw_g x_{c ^ 2^g}[rank][w]
 // which is exactly the sharded-qubit term that rank c needs for its chunk `rank`; rank c pulls it
 // back inside the fused H psi launch (kItemPeer).  Inbound per amplitude: 2 * 16 * (P-1)/P bytes.
 struct RemapArgs {
     const double2* xs[8];
     double2* z;
+    double hw[kMaxPeers];  // Omega/2 of the sharded qubit behind rank bit g
     int rank;
     int cbits;
 };
@@ -120,8 +140,12 @@ __global__ void __launch_bounds__(256) remap_z_kernel(const RemapArgs a) {
 #pragma unroll
         for (int c = 0; c < P; ++c) {
             double2 s = make_double2(0.0, 0.0);
+            int gi = 0;
 #pragma unroll
-            for (int g = 1; g < P; g <<= 1) cacc(s, v[c ^ g]);
+            for (int g = 1; g < P; g <<= 1, ++gi) {
+                s.x = fma(a.hw[gi], v[c ^ g].x, s.x);
+                s.y = fma(a.hw[gi], v[c ^ g].y, s.y);
+            }
             a.z[((u64)c << a.cbits) + w] = s;
         }
     }
@@ -164,112 +188,152 @@ QSB_DEV u64 ws_tile_base(int lb, int hb, int hb0, u64 tau) {
     return (outer << (hb0 + hb)) | (mid << lb);
 }
 
-// FIRST = contiguous tile (bits 0..TB-1 + diagonal + peers); otherwise strided rows (bits >= lb).
+QSB_DEV void cfma(double2& v, double c, double2 x) {
+    v.x = fma(c, x.x, v.x);
+    v.y = fma(c, x.y, v.y);
+}
+
+// FIRST = contiguous tile (index bits 0..TB-1 + diagonal + peers); otherwise strided rows (bits >= lb).
 // A thread owns tile indices idx = t + j * kGroupThreads (j = 0..7): tile bits [TB-3, TB) are
 // register-only flips, every other active tile bit is a conflict-free LDS.128 at an XOR-permuted
-// address.  Global operands (E_int or partial y, the Taylor accumulator, the first NVLink partner)
-// are requested up front with loads the compiler may not sink, so their latency hides behind the
-// shared-memory flip phase.
+// address.  Global operands (E or partial y, the first NVLink partner) are requested up front with
+// loads the compiler may not sink, so their latency hides behind the shared-memory flip phase.
 // PEER (FIRST only, sharded state): the producer has already pulled the partner tiles over NVLink
-// (kItemPeer stages, ws_peer below) and y holds (omega/2) * their sum; x is re-read from the tile at
-// the end instead of being kept live.
-template <int TB, bool FIRST, bool PEER>
-QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 base, bool last, int t, double& nrm) {
+// (kItemPeer stages, ws_peer below) and y holds sum_g hw_g * partner_g.
+// dsum: FIRST only -- sum of delta_q over the set bits of this thread's index t (bits 0..TB-4) plus
+// the tile's high part (WsItem::dhi).
+template <int TB, bool FIRST, bool PEER, bool LAST>
+QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 base, int t, double dsum, double& red) {
     using C = WsCfg<TB>;
     const int lb = FIRST ? TB : p.lb;
     const int hb0 = FIRST ? TB : p.hb0;
     const u64 low_mask = (1ull << lb) - 1ull;
     const int act_lo = FIRST ? 0 : lb;
-    const bool with_acc = last && p.acc != nullptr;
+    const int gshift = FIRST ? 0 : (hb0 - lb);  // tile bit b >= lb is index bit b + gshift
+    // Global index of amplitude j of this thread: the tile -> index map is a bit permutation, so
+    // g(t + j * 512) = (base | g(t)) + g(j * 512): ONE per-thread 64-bit base and eight warp-uniform
+    // offsets (compile-time constants for a contiguous tile) instead of eight live 64-bit addresses.
+    const u64 g0 = base | (FIRST ? (u64)t : (((((u64)t) >> lb) << hb0) | (((u64)t) & low_mask)));
 #define QSB_IDX(j) (t + (j)*C::kGroupThreads)
-#define QSB_GADDR(j) (base | ((((u64)QSB_IDX(j)) >> lb) << hb0) | (((u64)QSB_IDX(j)) & low_mask))
+#define QSB_GOFF(j) \
+    (FIRST ? (u64)((j)*C::kGroupThreads) : (((((u64)((j)*C::kGroupThreads)) >> lb) << hb0) | (((u64)((j)*C::kGroupThreads)) & low_mask)))
+#define QSB_GADDR(j) (g0 + QSB_GOFF(j))
 
-    double e[kPerThread];
-    double2 yv[kPerThread];  // non-FIRST: partial y; FIRST+PEER: first partner's amplitudes; FIRST: x
+    double e[FIRST ? kPerThread : 1];
+    double2 v[kPerThread];
+    if constexpr (FIRST) {
 #pragma unroll
-    for (int j = 0; j < kPerThread; ++j) {
-        if (FIRST) {
-            e[j] = ldnc1(p.eint + QSB_GADDR(j));
-            if (PEER) yv[j] = ldcg2(p.y + QSB_GADDR(j));  // (omega/2) * sum of partner amplitudes, left by the PEER items
-        } else {
-            yv[j] = ldcg2(p.y + QSB_GADDR(j));
-        }
+        for (int j = 0; j < kPerThread; ++j) e[j] = ldnc1(p.eint + QSB_GADDR(j));
     }
-    double2 sum[kPerThread];
+    // The accumulators START as the partial y (non-FIRST; L2-resident: written by the FIRST tiles of this
+    // super-block, or prefetched by the producer) or as the partners' term (FIRST + PEER): the loads
+    // land directly in v, there is no second copy to keep (or to spill) through the flip phases.
+    if constexpr (!FIRST || PEER) {
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) v[j] = ldcg2(p.y + QSB_GADDR(j));
+    } else {
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) v[j] = make_double2(0.0, 0.0);
+    }
     {
         double2 xv[kPerThread];
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) xv[j] = ts[QSB_IDX(j)];
+        // flips of the top three tile bits: partners are this thread's own registers
+        double hr[kRegBits];
+#pragma unroll
+        for (int b = 0; b < kRegBits; ++b) hr[b] = (C::kRegLo + b >= act_lo) ? p.sp.hw[C::kRegLo + b + gshift] : 0.0;
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) {
-            double2 a = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int b = 0; b < kRegBits; ++b)
-                if (C::kRegLo + b >= act_lo) cacc(a, xv[j ^ (1 << b)]);
-            sum[j] = a;
-        }
-        if (FIRST && !PEER) {
-#pragma unroll
-            for (int j = 0; j < kPerThread; ++j) yv[j] = xv[j];
+            // the three partner products first, y / zero last: the chain does not wait on the global load
+            double2 a = make_double2(hr[0] * xv[j ^ 1].x, hr[0] * xv[j ^ 1].y);
+            cfma(a, hr[1], xv[j ^ 2]);
+            cfma(a, hr[2], xv[j ^ 4]);
+            if constexpr (FIRST) {
+                // diagonal: d = E - sum_q delta_q b_q(k); bits TB-3..TB-1 of the index are j's bits
+                const double dj = ((j & 1) ? p.sp.dl[C::kRegLo] : 0.0) + ((j & 2) ? p.sp.dl[C::kRegLo + 1] : 0.0) +
+                                  ((j & 4) ? p.sp.dl[C::kRegLo + 2] : 0.0);
+                cfma(a, e[j] - (dsum + dj), xv[j]);
+            }
+            if constexpr (!FIRST || PEER) cacc(a, v[j]);
+            v[j] = a;
         }
     }
-    if (FIRST) {
+    if constexpr (FIRST) {
 #pragma unroll
         for (int b = 0; b < C::kRegLo; ++b) {
             const int tb = t ^ (1 << b);
+            const double h = p.sp.hw[b];
 #pragma unroll
-            for (int j = 0; j < kPerThread; ++j) cacc(sum[j], ts[tb + j * C::kGroupThreads]);
+            for (int j = 0; j < kPerThread; ++j) cfma(v[j], h, ts[tb + j * C::kGroupThreads]);
         }
     } else {
         for (int b = act_lo; b < C::kRegLo; ++b) {
             const int tb = t ^ (1 << b);
+            const double h = p.sp.hw[b + gshift];
 #pragma unroll
-            for (int j = 0; j < kPerThread; ++j) cacc(sum[j], ts[tb + j * C::kGroupThreads]);
+            for (int j = 0; j < kPerThread; ++j) cfma(v[j], h, ts[tb + j * C::kGroupThreads]);
         }
     }
-    // the accumulator was prefetched into L2 by the producer: load it only now (loading it before
-    // the flip phase made the compiler spill it, and the spill store waited on HBM)
-    double2 accv[kPerThread];
-    if (with_acc) {
+    // output addresses are formed only now (same trick): no 64-bit address lives through the flip phase
+    const u64 ge = g0 + ((u64)__double_as_longlong(v[0].x) & p.zero);
+    if constexpr (!LAST) {
 #pragma unroll
-        for (int j = 0; j < kPerThread; ++j) accv[j] = ldg2_volatile(p.acc + QSB_GADDR(j));
-    }
+        for (int j = 0; j < kPerThread; ++j) p.y[ge + QSB_GOFF(j)] = v[j];
+    } else {
+        // Taylor epilogue, in two batches of four amplitudes so that few addresses and accumulator
+        // values are in flight (the second batch's addresses depend on the first batch's results).
+        // The accumulator was prefetched into L2 by the producer: it is loaded only now.
+        const bool with_acc = p.acc_mode != kAccNone;
+        const double pairw = (p.acc_mode == kAccPair) ? 1.0 : 0.0;
+        const bool dot = p.red_mode == kRedDot;
+        const bool need_x = p.acc_mode == kAccPair || dot;
+        u64 chain = 0;
 #pragma unroll
-    for (int j = 0; j < kPerThread; ++j) {
-        const u64 g = QSB_GADDR(j);
-        double2 v;
-        if (FIRST) {
-            const double d = e[j] - p.delta * (double)(__popcll(g) + p.pop_rank);
-            const double2 xj = PEER ? ts[QSB_IDX(j)] : yv[j];
-            v = make_double2(d * xj.x + p.half_omega * sum[j].x, d * xj.y + p.half_omega * sum[j].y);
-            if (PEER) cacc(v, yv[j]);
-        } else {
-            v = make_double2(yv[j].x + p.half_omega * sum[j].x, yv[j].y + p.half_omega * sum[j].y);
+        for (int h = 0; h < kPerThread / 4; ++h) {
+            const u64 gb = g0 + (((u64)__double_as_longlong(v[4 * h].x) | chain) & p.zero);
+            double2 accv[4];
+            if (with_acc) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) accv[jj] = ldg2_volatile(p.acc + gb + QSB_GOFF(4 * h + jj));
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = 4 * h + jj;
+                const u64 g = gb + QSB_GOFF(j);
+                const double2 o = cmul(p.scale, v[j]);
+                double2 xo = make_double2(0.0, 0.0);
+                if (need_x) xo = ts[QSB_IDX(j)];
+                red += dot ? (xo.x * o.x + xo.y * o.y) : cnorm2(o);
+                if (with_acc) {
+                    double2 a = cadd(accv[jj], o);
+                    cfma(a, pairw, xo);
+                    p.acc[g] = a;
+                    chain |= (u64)__double_as_longlong(a.x);
+                }
+                p.y[g] = o;
+            }
         }
-        if (last) {
-            v = cmul(p.scale, v);
-            nrm += cnorm2(v);
-            if (with_acc) p.acc[g] = cadd(accv[j], v);
-        }
-        p.y[g] = v;
     }
 #undef QSB_GADDR
+#undef QSB_GOFF
 #undef QSB_IDX
 }
 
 // A partner GPU's tile (the sharded-qubit flip of the same 2^TB amplitudes), pulled over NVLink by
-// the producer's TMA copies into an ordinary stage: y = (omega/2) * partner  (first partner) or
-// y += (omega/2) * partner.  The FIRST item of the same tile follows in the same CTA, so the same
+// the producer's TMA copies into an ordinary stage: y = hw_g * partner  (first partner) or
+// y += hw_g * partner.  The FIRST item of the same tile follows in the same CTA, so the same
 // thread re-reads what it wrote: program order is the only synchronisation needed, and no consumer
 // ever stalls on an NVLink load -- the transfer latency sits in the stage ring like any other tile.
 template <int TB>
 QSB_DEV void ws_peer(const HpsiWs& p, const double2* __restrict__ ts, u64 base, int q, int t) {
     using C = WsCfg<TB>;
+    const double h = p.sp.hw_peer[q];
 #pragma unroll
     for (int j = 0; j < kPerThread; ++j) {
         const int idx = t + j * C::kGroupThreads;
         const double2 v = ts[idx];
-        double2 out = make_double2(p.half_omega * v.x, p.half_omega * v.y);
+        double2 out = make_double2(h * v.x, h * v.y);
         if (q > 0) cacc(out, ldcg2(p.y + base + idx));
         p.y[base + idx] = out;
     }
@@ -287,6 +351,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
     __shared__ WsItem desc[C::kStages];
     __shared__ int warps_done[C::kStages];
     __shared__ double red[32];
+    __shared__ int is_last_cta;
 
     const int t = threadIdx.x;
     const int warp = t >> 5, lane = t & 31;
@@ -302,10 +367,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
     }
     __syncthreads();
 
-    double nrm = 0.0;
+    double part = 0.0;
     if (warp >= kConsumerWarps) {
         // ================= producer warpgroup (only its first warp works) =================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == kConsumerWarps) {
             // Static schedule from ONE global ticket counter.  Tickets enumerate phases of n_a tiles:
             //   A(0) .. A(L-1),  then  A(s), B(s-L)  for s = L .. n_sb-1,  then  B(n_sb-L) .. B(n_sb-1)
@@ -333,26 +398,27 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                     type = peer_left > 0 ? kItemPeer : kItemFirst;
                     tau = pend_tau;
                 } else {
-                if (lane == 0 && n_done == 0) {
-                    const u64 ticket = atomicAdd(p.ticket, 1u);
-                    if (ticket < total) {
-                        if (!p.fused) {
-                            type = kItemPlain;
-                            tau = ticket;
-                        } else {
-                            type = ws_decode_ticket(ticket, n_a, n_sb, lag, (u64)p.sb_xor, &tau);
+                    if (lane == 0 && n_done == 0) {
+                        // the counter is never reset: this launch's tickets start at ticket_base (mod 2^32)
+                        const u64 ticket = (u64)(unsigned int)(atomicAdd(p.ticket, 1u) - p.ticket_base);
+                        if (ticket < total) {
+                            if (!p.fused) {
+                                type = kItemPlain;
+                                tau = ticket;
+                            } else {
+                                type = ws_decode_ticket(ticket, n_a, n_sb, lag, (u64)p.sb_xor, &tau);
+                            }
                         }
                     }
-                }
-                type = __shfl_sync(0xffffffffu, type, 0);
-                tau = __shfl_sync(0xffffffffu, tau, 0);
-                if (type == kItemFirst && p.n_peer > 0) {
-                    // sharded state: the partner tiles go first, one stage each, then the tile itself
-                    pend_tau = tau;
-                    peer_left = p.n_peer;
-                    first_pending = true;
-                    type = kItemPeer;
-                }
+                    type = __shfl_sync(0xffffffffu, type, 0);
+                    tau = __shfl_sync(0xffffffffu, tau, 0);
+                    if (type == kItemFirst && p.n_peer > 0) {
+                        // sharded state: the partner tiles go first, one stage each, then the tile itself
+                        pend_tau = tau;
+                        peer_left = p.n_peer;
+                        first_pending = true;
+                        type = kItemPeer;
+                    }
                 }
                 if (type == kItemPeer) {
                     const int q = p.n_peer - peer_left;
@@ -418,7 +484,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                             tma_load_2d(stage + ((size_t)(lane * 256) << p.lb), &tmap, c0, c1 + lane * 256, &full_bar[s]);
                         // the plain launch reads its partial y (and the accumulator) from HBM: start them now
                         if (type == kItemPlain && lane >= 8 && lane < 8 + n_box) tma_prefetch_2d(&tmap_y, c0, c1 + (lane - 8) * 256);
-                        if (type == kItemPlain && p.last && p.acc != nullptr && lane >= 16 && lane < 16 + n_box)
+                        if (type == kItemPlain && p.last && p.acc_mode != kAccNone && lane >= 16 && lane < 16 + n_box)
                             tma_prefetch_2d(&tmap_acc, c0, c1 + (lane - 16) * 256);
                     } else {
                         const uint32_t row_bytes = (uint32_t)(sizeof(double2) << p.lb);
@@ -427,12 +493,19 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                     }
                 }
                 if (lane == 0) {
+                    double dhi = 0.0;
+                    if (type == kItemFirst) {
+                        // detuning of the index bits above the tile (identical for its 2^TB amplitudes)
+                        dhi = p.sp.d_rank;
+                        for (u64 rest = base >> TB; rest; rest &= rest - 1ull) dhi += p.sp.dl[TB + __ffsll((long long)rest) - 1];
+                    }
                     if (type == kItemInner) {
                         // the partial y of this super-block must be complete (all its FIRST tiles stored)
                         while (ld_volatile_u64(p.done + sb) < p.done_target) __nanosleep(32);
                         __threadfence();  // acquire side of the done[] handshake
                     }
                     desc[s].base = base;
+                    desc[s].dhi = dhi;
                     desc[s].type = type;
                     desc[s].sb = sb;
                     mbar_arrive(&full_bar[s]);  // release: descriptor (and the INNER dependency) visible to consumers
@@ -445,6 +518,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
         asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         const int group = warp / C::kGroupWarps;
         const int tg = t - group * C::kGroupThreads;  // thread index within the group
+        // detuning of the index bits this thread's tile index fixes (bits 0..TB-4 of a FIRST tile)
+        double dlow = 0.0;
+#pragma unroll
+        for (int b = 0; b < C::kRegLo; ++b)
+            if ((tg >> b) & 1) dlow += p.sp.dl[b];
         for (u64 it = (u64)group;; it += C::kGroups) {
             const int s = (int)(it % C::kStages);
             const u64 use = it / C::kStages;
@@ -455,8 +533,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
             const int sb = desc[s].sb;
             const double2* ts = tiles + (size_t)s * C::kTileW;
             if (type == kItemFirst) {
-                if (p.n_peer > 0) ws_process<TB, true, true>(p, ts, base, false, tg, nrm);
-                else ws_process<TB, true, false>(p, ts, base, false, tg, nrm);
+                const double dsum = dlow + desc[s].dhi;
+                if (p.n_peer > 0) ws_process<TB, true, true, false>(p, ts, base, tg, dsum, part);
+                else ws_process<TB, true, false, false>(p, ts, base, tg, dsum, part);
                 // publish this tile of partial y: warp barrier -> cta-scope release on the shared
                 // counter; the last warp of the group to finish issues ONE gpu-scope fence (cumulative
                 // over the writes it observed through the counter) and bumps the super-block counter.
@@ -473,20 +552,36 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
             } else if (type == kItemPeer) {
                 ws_peer<TB>(p, ts, base, sb, tg);
             } else {
-                ws_process<TB, false, false>(p, ts, base, p.last != 0, tg, nrm);
+                if (p.last) ws_process<TB, false, false, true>(p, ts, base, tg, 0.0, part);
+                else ws_process<TB, false, false, false>(p, ts, base, tg, 0.0, part);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }
     }
-    // per-CTA norm partial (only meaningful when p.last)
-    nrm = warp_sum(nrm);
-    if (lane == 0) red[warp] = (warp < kConsumerWarps) ? nrm : 0.0;
+    if (p.norm_part == nullptr) return;  // uniform: only the launch that finishes a fused H psi reduces
+    // per-CTA partial, then the LAST CTA to arrive sums all partials in a fixed order (deterministic)
+    part = warp_sum(part);
+    if (lane == 0) red[warp] = (warp < kConsumerWarps) ? part : 0.0;
     __syncthreads();
-    if (t == 0 && p.norm_part != nullptr) {
+    if (t == 0) {
         double tot = 0.0;
         for (int w = 0; w < kConsumerWarps; ++w) tot += red[w];
         p.norm_part[blockIdx.x] = tot;
+        __threadfence();
+        const unsigned int arrived = atomicAdd(p.tail, 1u);
+        is_last_cta = (arrived == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (is_last_cta && warp == 0) {
+        __threadfence();
+        double s = 0.0;
+        for (int i = lane; i < (int)gridDim.x; i += 32) s += ld_volatile_f64(p.norm_part + i);
+        s = warp_sum(s);
+        if (lane == 0) {
+            *p.red_out = s;
+            *p.tail = 0u;  // ready for the next launch on this stream
+        }
     }
 }
 

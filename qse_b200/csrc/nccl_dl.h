@@ -14,7 +14,7 @@ typedef struct ncclComm* nccl_comm_t;
 typedef struct {
     char internal[128];
 } nccl_uid_t;
-enum { kNcclSuccess = 0 };
+enum { kNcclSuccess = 0, kNcclInProgress = 7 };
 enum { kNcclSum = 0, kNcclProd = 1, kNcclMax = 2, kNcclMin = 3 };
 enum { kNcclInt8 = 0, kNcclUint8 = 1, kNcclInt32 = 2, kNcclUint32 = 3, kNcclInt64 = 4, kNcclUint64 = 5,
        kNcclFloat16 = 6, kNcclFloat32 = 7, kNcclFloat64 = 8 };
@@ -31,6 +31,7 @@ struct NcclApi {
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
+    int (*CommGetAsyncError)(nccl_comm_t, int*) = nullptr;  // optional
     char why[256] = {0};
     bool ok = false;
 };
@@ -66,6 +67,7 @@ inline NcclApi* nccl_api() {
     QSB_NCCL_SYM(GroupEnd, "ncclGroupEnd")
     QSB_NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef QSB_NCCL_SYM
+    *(void**)(&api.CommGetAsyncError) = dlsym(api.handle, "ncclCommGetAsyncError");
     api.ok = true;
     return &api;
 }

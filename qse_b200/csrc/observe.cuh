@@ -201,19 +201,51 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(const double2* __restri
         if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffffull], 1u);
     }
 }
-// gather every entry with key > threshold, and those equal to it, into out (unordered)
-__global__ void __launch_bounds__(256) gather_ge_kernel(const double2* __restrict__ psi, u64 dim, u64 threshold,
+// gather every entry with key STRICTLY above the threshold into out (unordered)
+__global__ void __launch_bounds__(256) gather_gt_kernel(const double2* __restrict__ psi, u64 dim, u64 threshold,
                                                         u64 index_base, u64* out_idx, double* out_p,
                                                         unsigned int* counter, unsigned int cap) {
     for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < dim; k += (u64)gridDim.x * blockDim.x) {
         const double pk = cnorm2(psi[k]);
-        if ((u64)__double_as_longlong(pk) >= threshold) {
+        if ((u64)__double_as_longlong(pk) > threshold) {
             const unsigned int slot = atomicAdd(counter, 1u);
             if (slot < cap) {
                 out_idx[slot] = index_base + k;
                 out_p[slot] = pk;
             }
         }
+    }
+}
+// ties[i] = number of entries of chunk c0 + i (2^cb amplitudes each) whose key equals the threshold
+__global__ void __launch_bounds__(256) count_eq_kernel(const double2* __restrict__ psi, int cb, u64 c0, u64 n_chunks,
+                                                       u64 threshold, unsigned int* __restrict__ ties) {
+    __shared__ double red[32];
+    const u64 len = 1ull << cb;
+    for (u64 c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        double s = 0.0;  // exact for counts <= 2^16
+        for (u64 k = threadIdx.x; k < len; k += blockDim.x)
+            if ((u64)__double_as_longlong(cnorm2(psi[((c0 + c) << cb) + k])) == threshold) s += 1.0;
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) ties[c] = (unsigned int)s;
+    }
+}
+// one warp: the first `take` entries of one chunk whose key equals the threshold, in index order
+__global__ void take_eq_kernel(const double2* __restrict__ psi, int cb, u64 chunk, u64 threshold, u64 index_base,
+                               unsigned int take, u64* __restrict__ out_idx, double* __restrict__ out_p) {
+    const int lane = threadIdx.x & 31;
+    const u64 base = chunk << cb, len = 1ull << cb;
+    unsigned int found = 0;
+    for (u64 k0 = 0; k0 < len && found < take; k0 += 32) {
+        const u64 k = k0 + lane;
+        const double pk = (k < len) ? cnorm2(psi[base + k]) : -1.0;
+        const bool hit = (k < len) && (u64)__double_as_longlong(pk) == threshold;
+        const unsigned int m = __ballot_sync(0xffffffffu, hit);
+        const unsigned int pos = found + __popc(m & ((1u << lane) - 1u));
+        if (hit && pos < take) {
+            out_idx[pos] = index_base + base + k;
+            out_p[pos] = pk;
+        }
+        found += __popc(m);
     }
 }
 

@@ -18,6 +18,12 @@
 #include "nccl_dl.h"
 #include "observe.cuh"
 #include "small.cuh"
+#include "terms.cuh"
+
+#if __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>
+#define QSB_HAVE_NVTX 1
+#endif
 
 using namespace qsb;
 
@@ -50,7 +56,9 @@ struct qsb_ctx {
     int sb_lag = 0;     // lead of the FIRST tiles over the INNER tiles of the fused launch, in super-blocks
     int ws_tile_bits = 12;  // 12 (64 KiB tiles, 3 stages; measured best) or 11 (32 KiB tiles, 6 stages, two groups); 0 = fewest launches
     int sb_bits = 0;   // log2 of the L2-resident super-block (10 MiB each; 18 / lead 3 measured best on B200)
-    unsigned int* tickets = nullptr;        // one work counter per launch of an H psi
+    unsigned int* tickets = nullptr;        // one work counter per launch of an H psi (never reset: see ticket_base)
+    unsigned int ticket_base[16] = {0};     // host mirror: where the next launch's tickets start on each counter
+    unsigned int* tail = nullptr;           // CTAs that have stored their reduction partial (self-resetting)
     unsigned long long* sb_done = nullptr;  // per super-block completion counters (cumulative)
     unsigned long long ws_epoch = 0;
     int ws_sbits_active = -1;
@@ -64,6 +72,20 @@ struct qsb_ctx {
         CUtensorMap map;
     };
     std::vector<TmapEntry> tmaps;  // super-block size the completion counters were accumulated with
+    // per-site structure of H (README.md:93-95):
+    //   H = sum_q (Omega/2 w_omega[q] + x0[q]) X_q - sum_q delta w_delta[q] n_q + E + operator terms
+    //   w_omega / w_delta: qsb_set_site_weights (default 1);  t_omega / t_delta / x0: single-X / single-N strings
+    //   of qsb_set_operator_terms that fit the fast form (default 0)
+    double w_omega[QSB_MAX_QUBITS_DEV + 4], w_delta[QSB_MAX_QUBITS_DEV + 4], x0[QSB_MAX_QUBITS_DEV + 4];
+    double t_omega[QSB_MAX_QUBITS_DEV + 4], t_delta[QSB_MAX_QUBITS_DEV + 4];
+    std::vector<DiagTerm> diag_terms;       // static diagonal strings, added to E after the interaction
+    DiagTerm* diag_dev = nullptr;
+    // operator terms outside the fast form (terms.cuh), per rank
+    GenTerm* gen_dev = nullptr;
+    int n_gen = 0;
+    double gen_bound[3] = {0.0, 0.0, 0.0};  // sum |coef| per channel (spectral bound)
+    bool have_terms = false;                // qsb_set_operator_terms was called (E holds their static diagonal)
+    std::vector<double> v_host;             // last interaction matrix (E is rebuilt when the terms change)
     // options
     double tol = 1e-14, theta_max = 3.0;
     int max_terms = 64, fixed_terms = 0, force_flat = 0;
@@ -96,6 +118,19 @@ static int fail(qsb_ctx* c, int code, const char* fmt, ...) {
     snprintf(g_err, sizeof(g_err), "%s", buf);
     if (c) snprintf(c->err, sizeof(c->err), "%s", buf);
     return code;
+}
+
+static inline void nvtx_push(const char* name) {
+#ifdef QSB_HAVE_NVTX
+    nvtxRangePushA(name);
+#else
+    (void)name;
+#endif
+}
+static inline void nvtx_pop() {
+#ifdef QSB_HAVE_NVTX
+    nvtxRangePop();
+#endif
 }
 
 #define CU(call)                                                                                         \
@@ -144,11 +179,21 @@ static int rank_barrier(qsb_ctx* c) {
     if (c->nranks == 1) return QSB_OK;
     return allreduce(c, c->slots + c->slots_n - 1, 1, kNcclSum);
 }
+// asynchronous NCCL failures (a peer died, a transport error) surface here instead of as a hang
+static int nccl_async_check(qsb_ctx* c) {
+    if (c->nranks == 1 || !c->comm || !nccl_api()->CommGetAsyncError) return QSB_OK;
+    int async_err = kNcclSuccess;
+    const int r = nccl_api()->CommGetAsyncError(c->comm, &async_err);
+    if (r != kNcclSuccess) return fail(c, QSB_ERR_NCCL, "ncclCommGetAsyncError failed: %s", nccl_api()->GetErrorString(r));
+    if (async_err != kNcclSuccess && async_err != kNcclInProgress)
+        return fail(c, QSB_ERR_NCCL, "asynchronous NCCL error on rank %d: %s", c->rank, nccl_api()->GetErrorString(async_err));
+    return QSB_OK;
+}
 static int fetch_slots(qsb_ctx* c, size_t first, size_t count) {
     CU(cudaMemcpyAsync(c->h_slots + first, c->slots + first, count * sizeof(double), cudaMemcpyDeviceToHost,
                        c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    return QSB_OK;
+    return nccl_async_check(c);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -241,16 +286,75 @@ static int get_tmap(qsb_ctx* c, const double2* x, int lb, int hb, int hb0, const
     return QSB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// H(t) parameters: per-site drive / detuning in the index-bit layout the kernels use
+// ------------------------------------------------------------------------------------------------
+struct HParams {
+    SiteParams sp;
+    double hw_abs = 0.0;            // sum_q |hw_q|                      (spectral bound)
+    double d_pos = 0.0, d_neg = 0.0;  // sum_q max(delta_q, 0), sum_q max(-delta_q, 0)
+    double chan[3] = {1.0, 0.0, 0.0};  // scale of the operator terms of channel 0 (static), 1 (amplitude), 2 (detuning)
+};
+
+// hw_site[q], d_site[q] for q = 0..n-1 (qubit q <-> index bit n-1-q; bits >= nl are rank bits)
+static HParams hparams_from_sites(const qsb_ctx* c, const double* hw_site, const double* d_site, double amp, double det) {
+    HParams h;
+    memset(&h.sp, 0, sizeof(h.sp));
+    for (int q = 0; q < c->n; ++q) {
+        const int bit = c->n - 1 - q;
+        if (bit < c->nl) {
+            h.sp.hw[bit] = hw_site[q];
+            h.sp.dl[bit] = d_site[q];
+        } else {
+            const int g = bit - c->nl;
+            h.sp.hw_peer[g] = hw_site[q];
+            if ((c->rank >> g) & 1) h.sp.d_rank += d_site[q];
+        }
+        h.hw_abs += fabs(hw_site[q]);
+        h.d_pos += std::max(d_site[q], 0.0);
+        h.d_neg += std::max(-d_site[q], 0.0);
+    }
+    h.chan[0] = 1.0;
+    h.chan[1] = amp;
+    h.chan[2] = det;
+    return h;
+}
+// the global pulse of qse.calc.Qutip (qse/calc/qutip.py:55-58) through the per-site weights
+static HParams hparams_global(const qsb_ctx* c, double omega, double delta) {
+    double hw[QSB_MAX_QUBITS_DEV + 4], d[QSB_MAX_QUBITS_DEV + 4];
+    for (int q = 0; q < c->n; ++q) {
+        hw[q] = 0.5 * omega * (c->w_omega[q] + c->t_omega[q]) + c->x0[q];
+        d[q] = delta * (c->w_delta[q] + c->t_delta[q]);
+    }
+    return hparams_from_sites(c, hw, d, omega, delta);
+}
+// a per-site schedule row: omega_q and delta_q given for every qubit (weights still apply)
+static HParams hparams_rows(const qsb_ctx* c, const double* omega_q, const double* delta_q, double amp, double det) {
+    double hw[QSB_MAX_QUBITS_DEV + 4], d[QSB_MAX_QUBITS_DEV + 4];
+    for (int q = 0; q < c->n; ++q) {
+        hw[q] = 0.5 * (omega_q[q] * c->w_omega[q] + amp * c->t_omega[q]) + c->x0[q];
+        d[q] = delta_q[q] * c->w_delta[q] + det * c->t_delta[q];
+    }
+    return hparams_from_sites(c, hw, d, amp, det);
+}
+
+static unsigned int take_tickets(qsb_ctx* c, int counter, u64 total, int grid) {
+    // every launch performs exactly total + grid atomicAdds on its counter (one over-the-end ticket per CTA)
+    const unsigned int base = c->ticket_base[counter];
+    c->ticket_base[counter] = (unsigned int)(base + (unsigned int)total + (unsigned int)grid);
+    return base;
+}
+
 // warp-specialised path: one fused launch over L2-resident super-blocks + plain launches for the
 // index bits above the super-block (hpsi_ws.cuh)
-static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, double omega, double delta, bool fuse,
-                          double2 scale, double2* acc, double* norm_slot, const double2* const* peers) {
+static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, const HParams& hp, bool fuse, double2 scale,
+                          int acc_mode, int red_mode, double* red_slot, const double2* const* peers) {
     // partner stages and their FIRST stage must be consumed by the same threads: one consumer group
     const WsPlan w = make_ws_plan(c->nl, c->sb_bits, c->nranks > 1 ? 12 : c->ws_tile_bits);
     const u64 n_tiles = c->dim >> w.tb;
     const int grid = (int)std::min<u64>(n_tiles, (u64)c->n_sm);
-    CU(cudaMemsetAsync(c->tickets, 0, 16 * sizeof(unsigned int), c->stream));
     HpsiWs a{};
+    a.sp = hp.sp;
     // remap exchange: from 4 ranks up, when peer memory is mapped and a chunk holds whole tiles
     const bool remap = c->nranks >= 4 && c->nranks <= 8 && c->ipc && c->zbuf && c->exchange != 0 && (c->nl - c->p) >= w.tb;
     if (remap) {
@@ -260,30 +364,31 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, double omega
             if (!ra.xs[r]) return fail(c, QSB_ERR_STATE, "H psi input is not an exported buffer");
             a.zpeer[r] = c->peer_z[r];
         }
+        for (int g = 0; g < kMaxPeers; ++g) ra.hw[g] = hp.sp.hw_peer[g];
         ra.z = c->zbuf;
         ra.rank = c->rank;
         ra.cbits = c->nl - c->p;
         const int rgrid = grid_for(c, 1ull << ra.cbits, 256);
+        nvtx_push("qsb:remap_exchange");
         if (c->nranks == 4) remap_z_kernel<4><<<rgrid, 256, 0, c->stream>>>(ra);
         else remap_z_kernel<8><<<rgrid, 256, 0, c->stream>>>(ra);
         LAUNCHED(c);
         TRY(check_launch(c, "remap_z_kernel"));
         TRY(rank_barrier(c));  // every rank's Z must be complete before anyone pulls from it
+        nvtx_pop();
         a.remap = 1;
         a.rank = c->rank;
         a.cbits = ra.cbits;
         a.sb_xor = (ra.cbits >= w.sbits) ? ((unsigned int)c->rank << (ra.cbits - w.sbits)) : 0u;
+        for (int g = 0; g < kMaxPeers; ++g) a.sp.hw_peer[g] = 1.0;  // the coefficients are already in Z
     }
     a.x = x;
     a.y = y;
     a.eint = c->eint;
     for (int g = 0; g < kMaxPeers; ++g) a.peer[g] = peers[g];
     a.n_peer = remap ? 1 : c->p;
-    a.half_omega = 0.5 * omega;
-    a.delta = delta;
     a.scale = fuse ? scale : make_double2(1.0, 0.0);
     a.nl = c->nl;
-    a.pop_rank = c->pop_rank;
     a.done = c->sb_done;
     a.n_tiles = n_tiles;
     for (int i = 0; i <= w.n_plain; ++i) {
@@ -294,11 +399,17 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, double omega
         a.lb = g.lb;
         a.hb = g.hb;
         a.hb0 = g.hb0;
-        a.last = last ? 1 : 0;
+        a.last = (last && fuse) ? 1 : 0;
         a.lag = c->sb_lag > 0 ? c->sb_lag : auto_sb_lag(w.sbits);
-        a.acc = (fuse && last) ? acc : nullptr;
-        a.norm_part = (fuse && last && norm_slot) ? c->part : nullptr;
+        a.acc_mode = (fuse && last) ? acc_mode : kAccNone;
+        a.red_mode = red_mode;
+        a.acc = (a.acc_mode != kAccNone) ? c->psi : nullptr;
+        const bool reduce = fuse && last && red_slot;
+        a.norm_part = reduce ? c->part : nullptr;
+        a.red_out = reduce ? red_slot : nullptr;
+        a.tail = c->tail;
         a.ticket = c->tickets + i;
+        a.ticket_base = take_tickets(c, i, a.fused ? 2 * n_tiles : n_tiles, grid);
         if (i == 0) {
             if (c->ws_sbits_active != w.sbits * 16 + w.tb) {
                 // the counters are cumulative per super-block: a new block size starts a new count
@@ -330,20 +441,23 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, double omega
         LAUNCHED(c);
         TRY(check_launch(c, "hpsi_ws_kernel"));
     }
-    if (fuse && norm_slot) {
-        finalize_sum_kernel<<<1, 256, 0, c->stream>>>(c->part, grid, norm_slot);
-        LAUNCHED(c);
-        TRY(check_launch(c, "finalize_sum_kernel"));
-    }
     return QSB_OK;
 }
 
-// y <- scale * H(omega, delta) x   [fuse: acc += y (acc may be null), *norm_slot <- |y|^2 of this shard]
-static int launch_hpsi(qsb_ctx* c, const double2* x, double2* y, double omega, double delta, bool fuse,
-                       double2 scale, double2* acc, double* norm_slot) {
-    if (!c->have_v) return fail(c, QSB_ERR_STATE, "qsb_set_interaction has not been called");
+// y (+)= sum_t chan[t] coef_t P_t x for the operator terms that are not in the fast form (terms.cuh)
+static int launch_terms(qsb_ctx* c, const double2* x, double2* y, const HParams& hp);
+// out = scale * y;  reduction;  accumulator update -- the Taylor epilogue as a kernel of its own
+// (only needed when operator terms follow the fast H psi)
+static int launch_epilogue(qsb_ctx* c, const double2* x, double2* y, double2 scale, int acc_mode, int red_mode, double* red_slot);
+
+// y <- scale * (fast form of H) x   [fuse: + Taylor epilogue: acc_mode (kAcc*) into psi, *red_slot <- reduction
+// (kRed*) of this shard]
+static int launch_hpsi_core(qsb_ctx* c, const double2* x, double2* y, const HParams& hp, bool fuse, double2 scale,
+                            int acc_mode, int red_mode, double* red_slot) {
+    const bool fuse_here = fuse;
     const double2* peers[kMaxPeers] = {nullptr, nullptr, nullptr};
     if (c->p > kMaxPeers) return fail(c, QSB_ERR_UNSUPPORTED, "more than %d sharded qubits", kMaxPeers);
+    nvtx_push("qsb:hpsi");
     for (int g = 0; g < c->p; ++g) {
         const int partner = c->rank ^ (1 << g);
         if (c->ipc) {
@@ -354,67 +468,112 @@ static int launch_hpsi(qsb_ctx* c, const double2* x, double2* y, double omega, d
             NC(nccl_api()->Send(x, c->dim * 2, kNcclFloat64, partner, c->comm, c->stream));
             NC(nccl_api()->Recv(c->stage[g], c->dim * 2, kNcclFloat64, partner, c->comm, c->stream));
             NC(nccl_api()->GroupEnd());
+            TRY(nccl_async_check(c));
             peers[g] = c->stage[g];
         }
     }
     c->met.hpsi_calls++;
+    int rc = QSB_OK;
     if (!c->plan.tiled) {
         HpsiFlat a{};
         a.x = x;
         a.y = y;
         a.eint = c->eint;
-        a.acc = fuse ? acc : nullptr;
-        a.norm_part = (fuse && norm_slot) ? c->part : nullptr;
+        a.acc = (fuse_here && acc_mode != kAccNone) ? c->psi : nullptr;
+        a.norm_part = (fuse_here && red_slot) ? c->part : nullptr;
         for (int g = 0; g < kMaxPeers; ++g) a.peer[g] = peers[g];
         a.n_peer = c->p;
-        a.half_omega = 0.5 * omega;
-        a.delta = delta;
+        a.sp = hp.sp;
         a.scale = scale;
         a.nl = c->nl;
-        a.pop_rank = c->pop_rank;
-        a.fuse = fuse ? 1 : 0;
+        a.fuse = fuse_here ? 1 : 0;
+        a.acc_mode = fuse_here ? acc_mode : kAccNone;
+        a.red_mode = red_mode;
         const int grid = grid_for(c, c->dim, 256);
         hpsi_flat_kernel<<<grid, 256, 0, c->stream>>>(a);
         LAUNCHED(c);
-        TRY(check_launch(c, "hpsi_flat_kernel"));
-        if (fuse && norm_slot) {
-            finalize_sum_kernel<<<1, 256, 0, c->stream>>>(c->part, grid, norm_slot);
+        rc = check_launch(c, "hpsi_flat_kernel");
+        if (rc == QSB_OK && fuse_here && red_slot) {
+            finalize_sum_kernel<<<1, 256, 0, c->stream>>>(c->part, grid, red_slot);
             LAUNCHED(c);
+            rc = check_launch(c, "finalize_sum_kernel");
         }
-        return check_launch(c, "finalize_sum_kernel");
+    } else if (c->path == 0 && c->nl > kTileBits) {
+        rc = launch_hpsi_ws(c, x, y, hp, fuse_here, scale, acc_mode, red_mode, red_slot, peers);
+    } else {
+        const u64 n_tiles = c->dim >> kTileBits;
+        const int grid = (int)std::min<u64>(n_tiles, (u64)c->n_sm);
+        for (int i = 0; i < c->plan.n_pass && rc == QSB_OK; ++i) {
+            const bool first = (i == 0), last = (i == c->plan.n_pass - 1);
+            HpsiPass a{};
+            a.x = x;
+            a.y = y;
+            a.eint = c->eint;
+            a.acc_mode = (fuse_here && last) ? acc_mode : kAccNone;
+            a.red_mode = red_mode;
+            a.acc = (a.acc_mode != kAccNone) ? c->psi : nullptr;
+            a.norm_part = (fuse_here && last && red_slot) ? c->part : nullptr;
+            for (int g = 0; g < kMaxPeers; ++g) a.peer[g] = peers[g];
+            a.n_peer = first ? c->p : 0;
+            a.sp = hp.sp;
+            a.scale = fuse_here ? scale : make_double2(1.0, 0.0);
+            a.nl = c->nl;
+            a.lb = c->plan.pass[i].lb;
+            a.hb = c->plan.pass[i].hb;
+            a.hb0 = c->plan.pass[i].hb0;
+            a.n_tiles = n_tiles;
+            // LAST without fuse is a plain pass: scale = 1, no acc, no reduction
+            if (first && last) hpsi_tile_kernel<true, true><<<grid, kThreads, kTileSmemBytes, c->stream>>>(a);
+            else if (first) hpsi_tile_kernel<true, false><<<grid, kThreads, kTileSmemBytes, c->stream>>>(a);
+            else if (last) hpsi_tile_kernel<false, true><<<grid, kThreads, kTileSmemBytes, c->stream>>>(a);
+            else hpsi_tile_kernel<false, false><<<grid, kThreads, kTileSmemBytes, c->stream>>>(a);
+            LAUNCHED(c);
+            rc = check_launch(c, "hpsi_tile_kernel");
+        }
+        if (rc == QSB_OK && fuse_here && red_slot) {
+            finalize_sum_kernel<<<1, 256, 0, c->stream>>>(c->part, grid, red_slot);
+            LAUNCHED(c);
+            rc = check_launch(c, "finalize_sum_kernel");
+        }
     }
-    if (c->path == 0 && c->nl > kTileBits) return launch_hpsi_ws(c, x, y, omega, delta, fuse, scale, acc, norm_slot, peers);
-    const u64 n_tiles = c->dim >> kTileBits;
-    const int grid = (int)std::min<u64>(n_tiles, (u64)c->n_sm);
-    for (int i = 0; i < c->plan.n_pass; ++i) {
-        const bool first = (i == 0), last = (i == c->plan.n_pass - 1);
-        HpsiPass a{};
-        a.x = x;
-        a.y = y;
-        a.eint = c->eint;
-        a.acc = (fuse && last) ? acc : nullptr;
-        a.norm_part = (fuse && last && norm_slot) ? c->part : nullptr;
-        for (int g = 0; g < kMaxPeers; ++g) a.peer[g] = peers[g];
-        a.n_peer = first ? c->p : 0;
-        a.half_omega = 0.5 * omega;
-        a.delta = delta;
-        a.scale = fuse ? scale : make_double2(1.0, 0.0);
-        a.nl = c->nl;
-        a.lb = c->plan.pass[i].lb;
-        a.hb = c->plan.pass[i].hb;
-        a.hb0 = c->plan.pass[i].hb0;
-        a.pop_rank = c->pop_rank;
-        a.n_tiles = n_tiles;
-        // LAST without fuse is a plain pass: scale = 1, no acc, no norm
-        if (first && last) hpsi_tile_kernel<true, true><<<grid, kThreads, kTileSmemBytes, c->stream>>>(a);
-        else if (first) hpsi_tile_kernel<true, false><<<grid, kThreads, kTileSmemBytes, c->stream>>>(a);
-        else if (last) hpsi_tile_kernel<false, true><<<grid, kThreads, kTileSmemBytes, c->stream>>>(a);
-        else hpsi_tile_kernel<false, false><<<grid, kThreads, kTileSmemBytes, c->stream>>>(a);
-        LAUNCHED(c);
-        TRY(check_launch(c, "hpsi_tile_kernel"));
-    }
-    if (fuse && norm_slot) {
-        finalize_sum_kernel<<<1, 256, 0, c->stream>>>(c->part, grid, norm_slot);
+    nvtx_pop();
+    return rc;
+}
+
+// y <- scale * H x with H = fast form (E, per-site X and n) + operator terms, optionally followed by the
+// Taylor epilogue.  Without operator terms everything is ONE launch group with the epilogue fused in.
+static int launch_hpsi(qsb_ctx* c, const double2* x, double2* y, const HParams& hp, bool fuse, double2 scale,
+                       int acc_mode, int red_mode, double* red_slot) {
+    if (!c->have_v) return fail(c, QSB_ERR_STATE, "qsb_set_interaction has not been called");
+    if (c->n_gen == 0) return launch_hpsi_core(c, x, y, hp, fuse, scale, acc_mode, red_mode, red_slot);
+    TRY(launch_hpsi_core(c, x, y, hp, false, make_double2(1.0, 0.0), kAccNone, kRedNorm, nullptr));
+    TRY(launch_terms(c, x, y, hp));
+    if (fuse) TRY(launch_epilogue(c, x, y, scale, acc_mode, red_mode, red_slot));
+    return QSB_OK;
+}
+
+static int launch_terms(qsb_ctx* c, const double2* x, double2* y, const HParams& hp) {
+    TermsArgs a{};
+    a.terms = c->gen_dev;
+    a.n_terms = c->n_gen;
+    for (int r = 0; r < c->nranks && r < 8; ++r) a.xsrc[r] = (c->nranks == 1) ? x : peer_of(c, x, r);
+    a.xsrc[c->rank] = x;
+    a.y = y;
+    for (int i = 0; i < 3; ++i) a.chan[i] = hp.chan[i];
+    a.nl = c->nl;
+    terms_kernel<<<grid_for(c, c->dim, 256), 256, 0, c->stream>>>(a);
+    LAUNCHED(c);
+    return check_launch(c, "terms_kernel");
+}
+
+static int launch_epilogue(qsb_ctx* c, const double2* x, double2* y, double2 scale, int acc_mode, int red_mode,
+                           double* red_slot) {
+    const int grid = grid_for(c, c->dim, 256);
+    epilogue_kernel<<<grid, 256, 0, c->stream>>>(x, y, c->psi, scale, acc_mode, red_mode, c->dim, c->part);
+    LAUNCHED(c);
+    TRY(check_launch(c, "epilogue_kernel"));
+    if (red_slot) {
+        finalize_sum_kernel<<<1, 256, 0, c->stream>>>(c->part, grid, red_slot);
         LAUNCHED(c);
         TRY(check_launch(c, "finalize_sum_kernel"));
     }
@@ -424,20 +583,32 @@ static int launch_hpsi(qsb_ctx* c, const double2* x, double2* y, double omega, d
 // ------------------------------------------------------------------------------------------------
 // Taylor stepper (fused K4): psi <- sum_j (-i H dt)^j / j! psi, norm-terminated, sub-stepped
 // ------------------------------------------------------------------------------------------------
-static double spectral_bound(const qsb_ctx* c, double omega, double delta) {
-    const double hi = c->diag_max + std::max(-delta, 0.0) * c->n;
-    const double lo = c->diag_min - std::max(delta, 0.0) * c->n;
-    return std::max(fabs(hi), fabs(lo)) + 0.5 * fabs(omega) * c->n;
+static double spectral_bound(const qsb_ctx* c, const HParams& hp) {
+    const double hi = c->diag_max + hp.d_neg;
+    const double lo = c->diag_min - hp.d_pos;
+    return std::max(fabs(hi), fabs(lo)) + hp.hw_abs + c->gen_bound[0] + fabs(hp.chan[1]) * c->gen_bound[1] +
+           fabs(hp.chan[2]) * c->gen_bound[2];
 }
 
-static int copy_vec(qsb_ctx* c, double2* dst, const double2* src) {
-    copy_kernel<<<grid_for(c, c->dim, 256), 256, 0, c->stream>>>(dst, src, c->dim);
+static int axpy_vec(qsb_ctx* c, double2* acc, const double2* x) {
+    axpy_kernel<<<grid_for(c, c->dim, 256), 256, 0, c->stream>>>(acc, x, c->dim);
     LAUNCHED(c);
-    return check_launch(c, "copy_kernel");
+    return check_launch(c, "axpy_kernel");
 }
 
-static int evolve_segment_impl(qsb_ctx* c, double omega, double delta, double dt, int* n_hpsi) {
-    const double theta = spectral_bound(c, omega, delta) * fabs(dt);
+// One term x_j = (-i h / j) H x_{j-1} of the series, accumulated into psi as acc_mode says.
+static int taylor_term(qsb_ctx* c, const HParams& hp, double h, int j, int acc_mode, const double2** x_io) {
+    double2* y = (j & 1) ? c->wa : c->wb;
+    const double2 scale = make_double2(0.0, -h / (double)j);  // -i h / j
+    TRY(launch_hpsi(c, *x_io, y, hp, true, scale, acc_mode, kRedNorm, c->slots + j));
+    // the all-reduce doubles as the cross-rank barrier that orders peer reads of y
+    TRY(allreduce(c, c->slots + j, 1, kNcclSum));
+    *x_io = y;
+    return QSB_OK;
+}
+
+static int evolve_segment_impl(qsb_ctx* c, const HParams& hp, double dt, int* n_hpsi) {
+    const double theta = spectral_bound(c, hp) * fabs(dt);
     const int nsub = std::max(1, (int)ceil(theta / c->theta_max));
     const double h = dt / nsub;
     const double theta_sub = theta / nsub;
@@ -448,52 +619,51 @@ static int evolve_segment_impl(qsb_ctx* c, double omega, double delta, double dt
         if (n_hpsi) *n_hpsi = 0;
         return QSB_OK;
     }
-    // x may alias the accumulator psi only when every amplitude of x is read by the CTA that
-    // updates it, after the read: true for the tiled single-GPU path, false for the untiled
-    // kernel and whenever peers read x over NVLink while psi is being updated.
-    const bool need_copy = !c->plan.tiled || c->nranks > 1;
+    nvtx_push("qsb:segment");
     for (int sub = 0; sub < nsub; ++sub) {
         c->met.substeps++;
+        // Term 1 reads psi directly.  Terms are accumulated into psi in PAIRS -- the even term adds its
+        // input x_{j-1}, which sits in the tile it has just loaded, together with its output: ONE
+        // read-modify-write of psi per two terms -- so no term updates psi while it is an input, and
+        // neither the untiled kernel nor peers reading x over NVLink need a copy of psi.
         const double2* x = c->psi;
-        if (need_copy) {
-            TRY(copy_vec(c, c->wb, c->psi));
-            TRY(rank_barrier(c));  // partners must see the finished copy before they read it
-            x = c->wb;
-        }
-        bool converged = false;
-        int j = 1;
-        for (; j <= c->max_terms; ++j) {
-            double2* y = (j & 1) ? c->wa : c->wb;
-            const double2 scale = make_double2(0.0, -h / (double)j);  // -i h / j
-            double* slot = c->slots + j;
-            TRY(launch_hpsi(c, x, y, omega, delta, true, scale, c->psi, slot));
+        // Launch the number of terms the previous sub-step needed WITHOUT looking at the norms (no host
+        // round trip per term); a term beyond convergence is a legitimate (tiny) term of the series.
+        const int planned = c->fixed_terms > 0 ? c->fixed_terms : std::min(c->max_terms, std::max(1, c->m_prev));
+        for (int j = 1; j <= planned; ++j) {
+            int acc_mode = kAccPair;                     // even: psi += x_{j-1} + x_j
+            if (j & 1) acc_mode = (j < planned || j == 1) ? kAccNone : kAccTerm;  // odd: deferred, or the last one
+            TRY(taylor_term(c, hp, h, j, acc_mode, &x));
             ++applied;
-            // the all-reduce doubles as the cross-rank barrier that orders peer reads of y
-            TRY(allreduce(c, slot, 1, kNcclSum));
-            x = y;
-            if (c->fixed_terms > 0) {
-                if (j == c->fixed_terms) {
-                    converged = true;
-                    break;
-                }
-                continue;
-            }
-            if (j >= c->m_prev - 1) {
-                TRY(fetch_slots(c, j, 1));
+        }
+        if (planned == 1) TRY(axpy_vec(c, c->psi, x));  // x_0 IS psi: term 1 could not update it in place
+        int m = planned;
+        if (c->fixed_terms == 0) {
+            TRY(fetch_slots(c, 1, (size_t)planned));  // ONE synchronisation per sub-step
+            int conv = 0;
+            for (int j = 1; j <= planned && conv == 0; ++j) {
                 const double nrm = sqrt(c->h_slots[j]);
                 if (!(nrm == nrm)) return fail(c, QSB_ERR_NOCONV, "Taylor term %d is NaN (|H|dt bound %.3g)", j, theta_sub);
-                if (nrm <= c->tol && (double)j >= theta_sub) {
-                    converged = true;
-                    break;
-                }
+                if (nrm <= c->tol && (double)j >= theta_sub) conv = j;
             }
+            // not there yet: one more term at a time (psi is complete after every term from here on)
+            for (int j = planned + 1; conv == 0 && j <= c->max_terms; ++j) {
+                TRY(taylor_term(c, hp, h, j, kAccTerm, &x));
+                ++applied;
+                m = j;
+                TRY(fetch_slots(c, (size_t)j, 1));
+                const double nrm = sqrt(c->h_slots[j]);
+                if (!(nrm == nrm)) return fail(c, QSB_ERR_NOCONV, "Taylor term %d is NaN (|H|dt bound %.3g)", j, theta_sub);
+                if (nrm <= c->tol && (double)j >= theta_sub) conv = j;
+            }
+            if (conv == 0)
+                return fail(c, QSB_ERR_NOCONV, "Taylor series did not reach tol=%.1e in %d terms (|H|dt bound %.3g)",
+                            c->tol, c->max_terms, theta_sub);
+            c->m_prev = conv;
         }
-        if (!converged)
-            return fail(c, QSB_ERR_NOCONV, "Taylor series did not reach tol=%.1e in %d terms (|H|dt bound %.3g)",
-                        c->tol, c->max_terms, theta_sub);
-        c->m_prev = j;
-        c->met.last_terms = j;
+        c->met.last_terms = m;
     }
+    nvtx_pop();
     if (n_hpsi) *n_hpsi = applied;
     return QSB_OK;
 }
@@ -502,19 +672,22 @@ static int evolve_segment_impl(qsb_ctx* c, double omega, double delta, double dt
 // launch-bound sizes: the whole schedule in one single-CTA kernel (small.cuh)
 // ------------------------------------------------------------------------------------------------
 static bool small_schedule_ok(const qsb_ctx* c, const qsb_eops* eops) {
-    if (!c->small_kernel || c->nranks != 1 || c->nl > kSmallMaxQubits) return false;
+    if (!c->small_kernel || c->nranks != 1 || c->nl > kSmallMaxQubits || c->n_gen > 0) return false;
     if (eops)
         for (int o = 0; o < eops->n_ops; ++o)
             if (eops->ops[o].kind != QSB_EOP_ENERGY) return false;
     return true;
 }
 
+// site_stride: 0 = omega / delta hold one value per step, n = one row of n per-site values per step
 static int evolve_schedule_small(qsb_ctx* c, const double* omega, const double* delta, const double* dt_us,
-                                 int64_t n_steps, const qsb_eops* eops, double* expectations_out) {
+                                 int64_t n_steps, int site_stride, const qsb_eops* eops, double* expectations_out) {
     const int n_ops = eops ? eops->n_ops : 0;
-    // one device buffer: omega | delta | dt | eop_omega | eop_delta | expectations | info
-    const size_t n_sched = 3 * (size_t)n_steps, n_eop = 2 * (size_t)n_ops, n_exp = (size_t)n_steps * n_ops, n_info = 8;
-    const size_t need = n_sched + n_eop + n_exp + n_info;
+    const size_t row = site_stride ? (size_t)site_stride : 1;
+    // one device buffer: omega | delta | dt | eop_omega | eop_delta | w_omega | w_delta | x0 | expectations | info
+    const size_t n_od = (size_t)n_steps * row, n_sched = 2 * n_od + (size_t)n_steps, n_eop = 2 * (size_t)n_ops,
+                 n_site = 3 * (size_t)c->n, n_exp = (size_t)n_steps * n_ops, n_info = 8;
+    const size_t need = n_sched + n_eop + n_site + n_exp + n_info;
     if (need > c->sched_cap) {
         cudaFree(c->sched_dev);
         c->sched_dev = nullptr;
@@ -522,21 +695,27 @@ static int evolve_schedule_small(qsb_ctx* c, const double* omega, const double* 
         CU(cudaMalloc(&c->sched_dev, need * sizeof(double)));
         c->sched_cap = need;
     }
-    std::vector<double> host(n_sched + n_eop);
-    memcpy(host.data(), omega, n_steps * sizeof(double));
-    memcpy(host.data() + n_steps, delta, n_steps * sizeof(double));
-    memcpy(host.data() + 2 * n_steps, dt_us, n_steps * sizeof(double));
+    std::vector<double> host(n_sched + n_eop + n_site);
+    memcpy(host.data(), omega, n_od * sizeof(double));
+    memcpy(host.data() + n_od, delta, n_od * sizeof(double));
+    memcpy(host.data() + 2 * n_od, dt_us, n_steps * sizeof(double));
     for (int o = 0; o < n_ops; ++o) {
         host[n_sched + o] = eops->ops[o].omega;
         host[n_sched + n_ops + o] = eops->ops[o].delta;
+    }
+    for (int q = 0; q < c->n; ++q) {
+        host[n_sched + n_eop + q] = c->w_omega[q] + (site_stride ? 0.0 : c->t_omega[q]);
+        host[n_sched + n_eop + c->n + q] = c->w_delta[q] + (site_stride ? 0.0 : c->t_delta[q]);
+        host[n_sched + n_eop + 2 * c->n + q] = c->x0[q];
     }
     CU(cudaMemcpyAsync(c->sched_dev, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     SmallArgs a{};
     a.psi = c->psi;
     a.eint = c->eint;
     a.omega = c->sched_dev;
-    a.delta = c->sched_dev + n_steps;
-    a.dt = c->sched_dev + 2 * n_steps;
+    a.delta = c->sched_dev + n_od;
+    a.dt = c->sched_dev + 2 * n_od;
+    a.site_stride = site_stride;
     a.n_steps = n_steps;
     a.n = c->nl;
     a.tol = c->tol;
@@ -548,8 +727,11 @@ static int evolve_schedule_small(qsb_ctx* c, const double* omega, const double* 
     a.n_eops = n_ops;
     a.eop_omega = c->sched_dev + n_sched;
     a.eop_delta = c->sched_dev + n_sched + n_ops;
-    a.expect_out = c->sched_dev + n_sched + n_eop;
-    a.info = reinterpret_cast<unsigned long long*>(c->sched_dev + n_sched + n_eop + n_exp);
+    a.w_omega = c->sched_dev + n_sched + n_eop;
+    a.w_delta = a.w_omega + c->n;
+    a.x0 = a.w_delta + c->n;
+    a.expect_out = c->sched_dev + n_sched + n_eop + n_site;
+    a.info = reinterpret_cast<unsigned long long*>(c->sched_dev + n_sched + n_eop + n_site + n_exp);
     const size_t smem = 3 * sizeof(double2) << c->nl;
     evolve_small_kernel<<<1, kSmallThreads, smem, c->stream>>>(a);
     LAUNCHED(c);
@@ -585,6 +767,7 @@ static int pauli_batch(qsb_ctx* c, int64_t n_terms, const u64* xm, const u64* ym
     const size_t cap = (c->slots_n - 2) / 2;
     const int grid = grid_for(c, c->dim, 256);
     std::vector<double> sign;
+    u64 staged_flip = 0;  // sharded flip whose partner shard currently sits in stage[0] (no-IPC mode)
     for (int64_t t0 = 0; t0 < n_terms; t0 += (int64_t)cap) {
         const int64_t nb = std::min<int64_t>((int64_t)cap, n_terms - t0);
         sign.assign((size_t)nb, 0.0);  // 0: this shard contributes nothing to the term
@@ -599,16 +782,29 @@ static int pauli_batch(qsb_ctx* c, int64_t n_terms, const u64* xm, const u64* ym
             const u64 flip = x | y, zz = mode ? flip : (y | z);
             const u64 rank = (u64)c->rank;
             const u64 flip_g = flip >> c->nl, zz_g = zz >> c->nl, n_g = nmk >> c->nl;
+            const double2* bra = c->psi;
+            if (flip_g) {
+                if (c->ipc) {
+                    bra = c->peer_psi[rank ^ flip_g];
+                } else {
+                    // no peer mapping: stage the partner shard with ncclSend/Recv, as H psi does.  Every
+                    // rank takes part (before the N-projector test below, which is rank dependent); the
+                    // staged shard is reused by consecutive terms with the same sharded flip.
+                    if (staged_flip != flip_g) {
+                        const int partner = (int)(rank ^ flip_g);
+                        NC(nccl_api()->GroupStart());
+                        NC(nccl_api()->Send(c->psi, c->dim * 2, kNcclFloat64, partner, c->comm, c->stream));
+                        NC(nccl_api()->Recv(c->stage[0], c->dim * 2, kNcclFloat64, partner, c->comm, c->stream));
+                        NC(nccl_api()->GroupEnd());
+                        staged_flip = flip_g;
+                    }
+                    bra = c->stage[0];
+                }
+            }
             if ((rank & n_g) != n_g) continue;  // this shard has a 0 where N projects on 1
             PauliArgs a{};
             a.b = c->psi;
-            a.a = c->psi;
-            if (flip_g) {
-                if (!c->ipc)
-                    return fail(c, QSB_ERR_UNSUPPORTED,
-                                "Pauli term flips a sharded qubit and peer memory is not mapped");
-                a.a = c->peer_psi[rank ^ flip_g];
-            }
+            a.a = bra;
             a.flip = flip & lmask;
             a.zmask = zz & lmask;
             a.nmask = nmk & lmask;
@@ -692,18 +888,12 @@ static int marginals(qsb_ctx* c, double* tot, double* number /* n */, int cond_q
     return QSB_OK;
 }
 
-static int energy_impl(qsb_ctx* c, double omega, double delta, double* out) {
+// <psi|H|psi>: ONE H psi launch group whose last pass reduces Re conj(psi) (H psi) (no dot kernel)
+static int energy_impl(qsb_ctx* c, const HParams& hp, double* out) {
     TRY(rank_barrier(c));
-    TRY(launch_hpsi(c, c->psi, c->wa, omega, delta, false, make_double2(1.0, 0.0), nullptr, nullptr));
-    const int grid = grid_for(c, c->dim, 256);
-    dot_kernel<<<grid, 256, 0, c->stream>>>(c->psi, c->wa, c->dim, c->part);
-    LAUNCHED(c);
-    TRY(check_launch(c, "dot_kernel"));
-    finalize_pair_kernel<<<1, 256, 0, c->stream>>>(c->part, grid, c->slots);
-    LAUNCHED(c);
-    TRY(check_launch(c, "finalize_pair_kernel"));
-    TRY(allreduce(c, c->slots, 2, kNcclSum));
-    TRY(fetch_slots(c, 0, 2));
+    TRY(launch_hpsi(c, c->psi, c->wa, hp, true, make_double2(1.0, 0.0), kAccNone, kRedDot, c->slots));
+    TRY(allreduce(c, c->slots, 1, kNcclSum));
+    TRY(fetch_slots(c, 0, 1));
     *out = c->h_slots[0];
     return QSB_OK;
 }
@@ -826,8 +1016,9 @@ int qsb_create_sharded(int n_qubits, int device, int rank, int nranks, const voi
     if (!out) return fail(c, QSB_ERR_INVALID, "out is NULL");
     *out = nullptr;
     if (n_qubits < 1 || n_qubits > QSB_MAX_QUBITS) return fail(c, QSB_ERR_INVALID, "n_qubits=%d out of range", n_qubits);
-    if (nranks < 1 || (nranks & (nranks - 1)) || nranks > 64)
-        return fail(c, QSB_ERR_INVALID, "nranks=%d must be a power of two <= 64", nranks);
+    if (nranks < 1 || (nranks & (nranks - 1)) || nranks > (1 << kMaxPeers))
+        return fail(c, QSB_ERR_INVALID, "nranks=%d must be a power of two <= %d (at most %d sharded qubits)", nranks,
+                    1 << kMaxPeers, kMaxPeers);
     if (rank < 0 || rank >= nranks) return fail(c, QSB_ERR_INVALID, "rank=%d out of range", rank);
     int p = 0;
     while ((1 << p) < nranks) ++p;
@@ -848,6 +1039,11 @@ int qsb_create_sharded(int n_qubits, int device, int rank, int nranks, const voi
     c->dim = 1ull << c->nl;
     c->rank_bits = (u64)rank << c->nl;
     c->pop_rank = __builtin_popcount((unsigned)rank);
+    for (int q = 0; q < QSB_MAX_QUBITS_DEV + 4; ++q) {
+        c->w_omega[q] = 1.0;
+        c->w_delta[q] = 1.0;
+        c->x0[q] = c->t_omega[q] = c->t_delta[q] = 0.0;
+    }
     int rc = QSB_OK;
     do {
         cudaDeviceProp prop;
@@ -875,7 +1071,9 @@ int qsb_create_sharded(int n_qubits, int device, int rank, int nranks, const voi
         CUB(cudaFuncSetAttribute(hpsi_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
         CUB(cudaFuncSetAttribute(hpsi_ws_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes));
         CUB(cudaFuncSetAttribute(hpsi_ws_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes));
-        CUB(cudaMalloc(&c->tickets, 16 * sizeof(unsigned int)));
+        CUB(cudaMalloc(&c->tickets, 17 * sizeof(unsigned int)));
+        CUB(cudaMemset(c->tickets, 0, 17 * sizeof(unsigned int)));
+        c->tail = c->tickets + 16;
         CUB(cudaFuncSetAttribute(evolve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (int)sizeof(double2) << kSmallMaxQubits));
         {
             const size_t n_done = (size_t)(c->dim >> 13) + 1;
@@ -930,6 +1128,8 @@ int qsb_destroy(qsb_ctx* c) {
     cudaFree(c->flush_buf);
     cudaFree(c->topk_buf);
     cudaFree(c->tickets);
+    cudaFree(c->gen_dev);
+    cudaFree(c->diag_dev);
     cudaFree(c->sched_dev);
     cudaFree(c->sb_done);
     if (c->h_slots) cudaFreeHost(c->h_slots);
@@ -1004,22 +1204,24 @@ int qsb_set_option(qsb_ctx* c, const char* key, double value) {
     return QSB_OK;
 }
 
-int qsb_set_interaction(qsb_ctx* c, const double* v) {
-    if (!c || !v) return fail(c, QSB_ERR_INVALID, "NULL argument");
-    CU(cudaSetDevice(c->device));
+// E <- interaction diagonal (K1) + static diagonal operator strings; refresh its range
+static int rebuild_diagonal(qsb_ctx* c) {
     const int n = c->n;
-    std::vector<double> tab((size_t)n * n, 0.0);
-    for (int i = 0; i < n; ++i)
-        for (int j = i + 1; j < n; ++j) {
-            const double x = v[(size_t)i * n + j];
-            if (!(x == x) || isinf(x)) return fail(c, QSB_ERR_INVALID, "V[%d,%d] is not finite", i, j);
-            tab[(size_t)i * n + j] = x;
-        }
-    CU(cudaMemcpyAsync(c->vtab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->vtab, c->v_host.data(), c->v_host.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     const int grid = grid_for(c, c->dim, 256);
     diag_build_kernel<<<grid, 256, (size_t)n * n * sizeof(double), c->stream>>>(c->eint, c->vtab, n, c->nl, c->rank_bits);
     LAUNCHED(c);
     TRY(check_launch(c, "diag_build_kernel"));
+    if (!c->diag_terms.empty()) {
+        cudaFree(c->diag_dev);
+        c->diag_dev = nullptr;
+        CU(cudaMalloc(&c->diag_dev, c->diag_terms.size() * sizeof(DiagTerm)));
+        CU(cudaMemcpyAsync(c->diag_dev, c->diag_terms.data(), c->diag_terms.size() * sizeof(DiagTerm), cudaMemcpyHostToDevice,
+                           c->stream));
+        diag_terms_kernel<<<grid, 256, 0, c->stream>>>(c->eint, c->diag_dev, (int)c->diag_terms.size(), c->nl, c->rank_bits);
+        LAUNCHED(c);
+        TRY(check_launch(c, "diag_terms_kernel"));
+    }
     minmax_kernel<<<grid, 256, 0, c->stream>>>(c->eint, c->dim, c->part);
     LAUNCHED(c);
     TRY(check_launch(c, "minmax_kernel"));
@@ -1042,6 +1244,116 @@ int qsb_set_interaction(qsb_ctx* c, const double* v) {
     c->have_v = true;
     c->m_prev = 0;
     return QSB_OK;
+}
+
+int qsb_set_interaction(qsb_ctx* c, const double* v) {
+    if (!c || !v) return fail(c, QSB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    const int n = c->n;
+    std::vector<double> tab((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j) {
+            const double x = v[(size_t)i * n + j];
+            if (!(x == x) || isinf(x)) return fail(c, QSB_ERR_INVALID, "V[%d,%d] is not finite", i, j);
+            tab[(size_t)i * n + j] = x;
+        }
+    c->v_host.swap(tab);
+    return rebuild_diagonal(c);
+}
+
+int qsb_set_site_weights(qsb_ctx* c, const double* w_omega, const double* w_delta) {
+    if (!c) return fail(c, QSB_ERR_INVALID, "NULL context");
+    for (int q = 0; q < c->n; ++q) {
+        const double a = w_omega ? w_omega[q] : 1.0, b = w_delta ? w_delta[q] : 1.0;
+        if (!(a == a) || isinf(a) || !(b == b) || isinf(b)) return fail(c, QSB_ERR_INVALID, "site weight %d is not finite", q);
+        c->w_omega[q] = a;
+        c->w_delta[q] = b;
+    }
+    c->m_prev = 0;
+    return QSB_OK;
+}
+
+int qsb_set_operator_terms(qsb_ctx* c, int64_t n_terms, const double* coef, const uint64_t* xmask, const uint64_t* ymask,
+                           const uint64_t* zmask, const uint64_t* nmask, const int32_t* channel) {
+    if (!c || n_terms < 0 || (n_terms > 0 && (!coef || !xmask || !ymask || !zmask || !nmask)))
+        return fail(c, QSB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    const u64 lmask = c->dim - 1ull;
+    std::vector<GenTerm> gen;
+    std::vector<DiagTerm> diag;
+    double t_omega[QSB_MAX_QUBITS_DEV + 4] = {0}, t_delta[QSB_MAX_QUBITS_DEV + 4] = {0}, x0[QSB_MAX_QUBITS_DEV + 4] = {0};
+    double bound[3] = {0.0, 0.0, 0.0};
+    for (int64_t t = 0; t < n_terms; ++t) {
+        const u64 x = xmask[t], y = ymask[t], z = zmask[t], nm = nmask[t];
+        const int ch = channel ? channel[t] : 0;
+        if (ch < 0 || ch > 2) return fail(c, QSB_ERR_INVALID, "operator term %lld: channel must be 0, 1 or 2", (long long)t);
+        if ((x & y) | (x & z) | (x & nm) | (y & z) | (y & nm) | (z & nm))
+            return fail(c, QSB_ERR_INVALID, "operator term %lld: masks overlap", (long long)t);
+        if ((x | y | z | nm) >> c->n) return fail(c, QSB_ERR_INVALID, "operator term %lld: mask beyond qubit count", (long long)t);
+        if (!(coef[t] == coef[t]) || isinf(coef[t])) return fail(c, QSB_ERR_INVALID, "operator term %lld: coefficient is not finite", (long long)t);
+        if (coef[t] == 0.0) continue;
+        const u64 flip = x | y;
+        const bool single_x = y == 0 && z == 0 && nm == 0 && __builtin_popcountll(x) == 1;
+        const bool single_n = x == 0 && y == 0 && z == 0 && __builtin_popcountll(nm) == 1;
+        if (single_x && ch != 2) {  // per-site drive: static, or scaled by the amplitude (H_amp = 0.5 X is coef 0.5)
+            const int q = c->n - 1 - (63 - __builtin_clzll(x));
+            if (ch == 0) x0[q] += coef[t];
+            else t_omega[q] += 2.0 * coef[t];
+            continue;
+        }
+        if (single_n && ch == 2) {  // per-site detuning: H_det = -1.0 N is coef -1
+            const int q = c->n - 1 - (63 - __builtin_clzll(nm));
+            t_delta[q] += -coef[t];
+            continue;
+        }
+        if (flip == 0 && ch == 0) {  // static diagonal string: folded into E
+            diag.push_back(DiagTerm{coef[t], z, nm});
+            continue;
+        }
+        // generic term, per rank: source shard, sign of the sharded Z / Y bits, sharded N projector
+        const u64 flip_g = flip >> c->nl, zy_g = (y | z) >> c->nl, n_g = nm >> c->nl;
+        bound[ch] += fabs(coef[t]);
+        if (flip_g && c->nranks > 1 && !c->ipc)
+            return fail(c, QSB_ERR_UNSUPPORTED, "operator term %lld flips a sharded qubit and peer memory is not mapped", (long long)t);
+        if (((u64)c->rank & n_g) != n_g) continue;
+        const u64 src = (u64)c->rank ^ flip_g;
+        GenTerm g{};
+        g.coef = (__builtin_popcountll(src & zy_g) & 1) ? -coef[t] : coef[t];
+        g.flip = flip & lmask;
+        g.zy = (y | z) & lmask;
+        g.nm = nm & lmask;
+        g.ny = __builtin_popcountll(y) & 3;
+        g.chan = ch;
+        g.src = (int)src;
+        gen.push_back(g);
+    }
+    cudaFree(c->gen_dev);
+    c->gen_dev = nullptr;
+    c->n_gen = 0;
+    if (!gen.empty()) {
+        CU(cudaMalloc(&c->gen_dev, gen.size() * sizeof(GenTerm)));
+        CU(cudaMemcpyAsync(c->gen_dev, gen.data(), gen.size() * sizeof(GenTerm), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    // every rank must take the same code path (the terms kernel is not a collective, but the stepper's
+    // launch sequence is): the count that matters is "any generic term in the register", not per rank
+    c->n_gen = (bound[0] + bound[1] + bound[2] > 0.0) ? std::max<int>(1, (int)gen.size()) : 0;
+    if (c->n_gen && gen.empty()) {
+        GenTerm zero{};  // this rank holds none of them: a single null term keeps the launch sequence uniform
+        zero.src = c->rank;
+        CU(cudaMalloc(&c->gen_dev, sizeof(GenTerm)));
+        CU(cudaMemcpy(c->gen_dev, &zero, sizeof(GenTerm), cudaMemcpyHostToDevice));
+    }
+    for (int i = 0; i < 3; ++i) c->gen_bound[i] = bound[i];
+    for (int q = 0; q < c->n; ++q) {
+        c->t_omega[q] = t_omega[q];
+        c->t_delta[q] = t_delta[q];
+        c->x0[q] = x0[q];
+    }
+    c->diag_terms.swap(diag);
+    c->have_terms = n_terms > 0;
+    if (c->v_host.empty()) c->v_host.assign((size_t)c->n * c->n, 0.0);
+    return rebuild_diagonal(c);
 }
 
 int qsb_get_diagonal(qsb_ctx* c, double* out) {
@@ -1084,8 +1396,21 @@ int qsb_apply_h(qsb_ctx* c, double omega, double delta) {
     if (!c) return fail(c, QSB_ERR_INVALID, "NULL context");
     CU(cudaSetDevice(c->device));
     TRY(rank_barrier(c));
-    TRY(launch_hpsi(c, c->psi, c->wa, omega, delta, false, make_double2(1.0, 0.0), nullptr, nullptr));
+    TRY(launch_hpsi(c, c->psi, c->wa, hparams_global(c, omega, delta), false, make_double2(1.0, 0.0), kAccNone, kRedNorm, nullptr));
     TRY(rank_barrier(c));
+    CU(cudaStreamSynchronize(c->stream));
+    return QSB_OK;
+}
+
+int qsb_apply_h_to(qsb_ctx* c, double omega, double delta, const double* in_re_im, double* out_re_im) {
+    if (!c || !in_re_im || !out_re_im) return fail(c, QSB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    // through the work vectors only: the evolved state (psi) is left untouched
+    CU(cudaMemcpyAsync(c->wb, in_re_im, c->dim * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+    TRY(rank_barrier(c));  // partners read wb over NVLink
+    TRY(launch_hpsi(c, c->wb, c->wa, hparams_global(c, omega, delta), false, make_double2(1.0, 0.0), kAccNone, kRedNorm, nullptr));
+    TRY(rank_barrier(c));
+    CU(cudaMemcpyAsync(out_re_im, c->wa, c->dim * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return QSB_OK;
 }
@@ -1102,7 +1427,7 @@ int qsb_evolve_segment(qsb_ctx* c, double omega, double delta, double dt_us, int
     if (!c) return fail(c, QSB_ERR_INVALID, "NULL context");
     if (!c->have_v) return fail(c, QSB_ERR_STATE, "qsb_set_interaction has not been called");
     CU(cudaSetDevice(c->device));
-    TRY(evolve_segment_impl(c, omega, delta, dt_us, n_hpsi));
+    TRY(evolve_segment_impl(c, hparams_global(c, omega, delta), dt_us, n_hpsi));
     CU(cudaStreamSynchronize(c->stream));
     return QSB_OK;
 }
@@ -1122,22 +1447,35 @@ int qsb_expect_pauli(qsb_ctx* c, int64_t n_terms, const double* coef, const uint
     return QSB_OK;
 }
 
-int qsb_evolve_schedule(qsb_ctx* c, const double* omega, const double* delta, const double* dt_us, int64_t n_steps,
-                        const qsb_eops* eops, double* expectations_out) {
+// the loop of Qutip.calculate; site_stride 0: one (omega, delta) per step, n: one row of per-site values per step
+static int evolve_schedule_impl(qsb_ctx* c, const double* omega, const double* delta, const double* dt_us, int64_t n_steps,
+                                int site_stride, const qsb_eops* eops, double* expectations_out) {
     if (!c || (n_steps > 0 && (!omega || !delta || !dt_us))) return fail(c, QSB_ERR_INVALID, "NULL argument");
     if (!c->have_v) return fail(c, QSB_ERR_STATE, "qsb_set_interaction has not been called");
     const int n_ops = eops ? eops->n_ops : 0;
     if (n_ops > 0 && !expectations_out) return fail(c, QSB_ERR_INVALID, "expectations_out is NULL");
     CU(cudaSetDevice(c->device));
-    if (n_steps > 0 && small_schedule_ok(c, eops)) return evolve_schedule_small(c, omega, delta, dt_us, n_steps, eops, expectations_out);
+    if (n_steps > 0 && small_schedule_ok(c, eops))
+        return evolve_schedule_small(c, omega, delta, dt_us, n_steps, site_stride, eops, expectations_out);
     std::vector<TermResult> res;
     for (int64_t s = 0; s < n_steps; ++s) {
-        TRY(evolve_segment_impl(c, omega[s], delta[s], dt_us[s], nullptr));
+        if (site_stride) {
+            // channel scales of the operator terms under a per-site schedule: the site average of the row
+            double amp = 0.0, det = 0.0;
+            for (int q = 0; q < c->n; ++q) {
+                amp += omega[s * site_stride + q];
+                det += delta[s * site_stride + q];
+            }
+            TRY(evolve_segment_impl(c, hparams_rows(c, omega + s * site_stride, delta + s * site_stride, amp / c->n, det / c->n),
+                                    dt_us[s], nullptr));
+        } else {
+            TRY(evolve_segment_impl(c, hparams_global(c, omega[s], delta[s]), dt_us[s], nullptr));
+        }
         for (int o = 0; o < n_ops; ++o) {
             const qsb_eop& op = eops->ops[o];
             double val = 0.0;
             if (op.kind == QSB_EOP_ENERGY) {
-                TRY(energy_impl(c, op.omega, op.delta, &val));
+                TRY(energy_impl(c, hparams_global(c, op.omega, op.delta), &val));
             } else if (op.kind == QSB_EOP_PAULI) {
                 if (op.term_begin < 0 || op.term_end > eops->n_terms || op.term_begin > op.term_end)
                     return fail(c, QSB_ERR_INVALID, "e_op %d: bad term range", o);
@@ -1158,6 +1496,17 @@ int qsb_evolve_schedule(qsb_ctx* c, const double* omega, const double* delta, co
     return QSB_OK;
 }
 
+int qsb_evolve_schedule(qsb_ctx* c, const double* omega, const double* delta, const double* dt_us, int64_t n_steps,
+                        const qsb_eops* eops, double* expectations_out) {
+    return evolve_schedule_impl(c, omega, delta, dt_us, n_steps, 0, eops, expectations_out);
+}
+
+int qsb_evolve_schedule_sites(qsb_ctx* c, const double* omega_sites, const double* delta_sites, const double* dt_us,
+                              int64_t n_steps, const qsb_eops* eops, double* expectations_out) {
+    if (!c) return fail(c, QSB_ERR_INVALID, "NULL context");
+    return evolve_schedule_impl(c, omega_sites, delta_sites, dt_us, n_steps, c->n, eops, expectations_out);
+}
+
 int qsb_norm(qsb_ctx* c, double* out) {
     if (!c || !out) return fail(c, QSB_ERR_INVALID, "NULL argument");
     CU(cudaSetDevice(c->device));
@@ -1168,7 +1517,7 @@ int qsb_energy(qsb_ctx* c, double omega, double delta, double* out) {
     if (!c || !out) return fail(c, QSB_ERR_INVALID, "NULL argument");
     if (!c->have_v) return fail(c, QSB_ERR_STATE, "qsb_set_interaction has not been called");
     CU(cudaSetDevice(c->device));
-    return energy_impl(c, omega, delta, out);
+    return energy_impl(c, hparams_global(c, omega, delta), out);
 }
 
 int qsb_number(qsb_ctx* c, double* out) {
@@ -1301,19 +1650,50 @@ int qsb_topk_probs(qsb_ctx* c, int k, uint64_t* idx, double* prob) {
         prefix |= (u64)b << shift;
         pmask |= 0xffffull << shift;
     }
-    // gather everything >= threshold (ties may exceed kk); capacity bounded by the scratch buffer
+    // `prefix` is now the key of the kk-th largest probability and `want` the number of entries EQUAL to
+    // it that still belong to the top kk (the others are strictly larger).  Gather the strictly larger
+    // ones (at most kk - want <= cap), then the `want` ties of LOWEST index in index order: a sparse
+    // state (all ties at probability 0, e.g. |0...0> or an empty shard) costs nothing extra.
     u64* d_idx = reinterpret_cast<u64*>(c->topk_buf + hist_bytes);
     double* d_p = reinterpret_cast<double*>(c->topk_buf + hist_bytes) + cap;
     unsigned int* d_count = reinterpret_cast<unsigned int*>(c->slots);
     CU(cudaMemsetAsync(d_count, 0, sizeof(double), c->stream));
-    gather_ge_kernel<<<grid, 256, 0, c->stream>>>(c->psi, c->dim, prefix, c->rank_bits, d_idx, d_p, d_count, cap);
+    gather_gt_kernel<<<grid, 256, 0, c->stream>>>(c->psi, c->dim, prefix, c->rank_bits, d_idx, d_p, d_count, cap);
     LAUNCHED(c);
-    TRY(check_launch(c, "gather_ge_kernel"));
+    TRY(check_launch(c, "gather_gt_kernel"));
     unsigned int count = 0;
     CU(cudaMemcpyAsync(&count, d_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (count > cap)
-        return fail(c, QSB_ERR_UNSUPPORTED, "top-k: %u amplitudes tie at the k-th probability (capacity %u)", count, cap);
+    if ((u64)count + want != kk || count > cap)  // cannot happen: the radix select counted exactly these
+        return fail(c, QSB_ERR_STATE, "top-k: %u entries above the threshold, %llu ties wanted, k = %llu", count,
+                    (unsigned long long)want, (unsigned long long)kk);
+    {
+        // ties in index order: per-chunk tie counts -> host prefix -> the chunks that hold the first `want`
+        const int cb = std::min(c->nl, 16);
+        const u64 n_chunks = c->dim >> cb;
+        unsigned int* d_tie = hist;  // the histogram is free again (n_chunks <= 65536 ... else several rounds)
+        std::vector<unsigned int> tie(65536);
+        u64 found = 0;
+        for (u64 c0 = 0; c0 < n_chunks && found < want; c0 += 65536) {
+            const u64 nc = std::min<u64>(65536, n_chunks - c0);
+            count_eq_kernel<<<(int)std::min<u64>(nc, (u64)c->n_sm * 8), 256, 0, c->stream>>>(c->psi, cb, c0, nc, prefix, d_tie);
+            LAUNCHED(c);
+            TRY(check_launch(c, "count_eq_kernel"));
+            CU(cudaMemcpyAsync(tie.data(), d_tie, nc * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            for (u64 i = 0; i < nc && found < want; ++i) {
+                if (tie[i] == 0) continue;
+                const unsigned int take = (unsigned int)std::min<u64>(tie[i], want - found);
+                take_eq_kernel<<<1, 32, 0, c->stream>>>(c->psi, cb, c0 + i, prefix, c->rank_bits, take, d_idx + count + found,
+                                                        d_p + count + found);
+                LAUNCHED(c);
+                TRY(check_launch(c, "take_eq_kernel"));
+                found += take;
+            }
+        }
+        if (found != want) return fail(c, QSB_ERR_STATE, "top-k: tie scan found %llu of %llu", (unsigned long long)found, (unsigned long long)want);
+        count += (unsigned int)want;
+    }
     std::vector<u64> hi(count);
     std::vector<double> hp(count);
     CU(cudaMemcpyAsync(hi.data(), d_idx, count * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
@@ -1524,7 +1904,7 @@ int qsb_time_apply_h(qsb_ctx* c, double omega, double delta, int iters, int do_f
         if (do_flush) TRY(flush_l2(c));
         TRY(rank_barrier(c));
         CU(cudaEventRecord(c->ev0, c->stream));
-        TRY(launch_hpsi(c, c->psi, c->wa, omega, delta, false, make_double2(1.0, 0.0), nullptr, nullptr));
+        TRY(launch_hpsi(c, c->psi, c->wa, hparams_global(c, omega, delta), false, make_double2(1.0, 0.0), kAccNone, kRedNorm, nullptr));
         CU(cudaEventRecord(c->ev1, c->stream));
         CU(cudaEventSynchronize(c->ev1));
         CU(cudaEventElapsedTime(&ms_each[i], c->ev0, c->ev1));
@@ -1541,7 +1921,7 @@ int qsb_time_schedule(qsb_ctx* c, const double* omega, const double* delta, cons
     CU(cudaSetDevice(c->device));
     for (int64_t s = 0; s < n_steps; ++s) {
         CU(cudaEventRecord(c->ev0, c->stream));
-        TRY(evolve_segment_impl(c, omega[s], delta[s], dt_us[s], nullptr));
+        TRY(evolve_segment_impl(c, hparams_global(c, omega[s], delta[s]), dt_us[s], nullptr));
         CU(cudaEventRecord(c->ev1, c->stream));
         CU(cudaEventSynchronize(c->ev1));
         CU(cudaEventElapsedTime(&ms_each[s], c->ev0, c->ev1));

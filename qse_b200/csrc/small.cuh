@@ -17,9 +17,13 @@ constexpr int kSmallThreads = 1024;
 struct SmallArgs {
     double2* psi;          // in/out (global)
     const double* eint;    // interaction diagonal (global)
-    const double* omega;
+    const double* omega;   // [n_steps] (site_stride 0) or [n_steps * n] (site_stride n): per-site schedule rows
     const double* delta;
     const double* dt;
+    const double* w_omega; // [n] per-site weights and static X coefficients (README.md:93-95 Hamiltonian)
+    const double* w_delta;
+    const double* x0;
+    int site_stride;
     long long n_steps;
     int n;
     double tol, theta_max;
@@ -54,6 +58,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) evolve_small_kernel(const Sm
     double2* yb = ya + dim;
     __shared__ double red[32];
     __shared__ double bcast;
+    __shared__ double hw_s[kSmallMaxQubits], d_s[kSmallMaxQubits];  // per index bit: Omega_q / 2, delta_q
     const int tid = threadIdx.x;
 
     for (int k = tid; k < dim; k += kSmallThreads) psi[k] = a.psi[k];
@@ -61,10 +66,23 @@ __global__ void __launch_bounds__(kSmallThreads, 1) evolve_small_kernel(const Sm
 
     unsigned long long n_hpsi = 0, n_sub = 0, last_terms = 0, err = 0, err_step = 0;
     for (long long s = 0; s < a.n_steps && !err; ++s) {
-        const double omega = a.omega[s], delta = a.delta[s], dt = a.dt[s];
-        const double half_omega = 0.5 * omega;
-        const double hi = a.diag_max + fmax(-delta, 0.0) * a.n, lo = a.diag_min - fmax(delta, 0.0) * a.n;
-        const double theta = (fmax(fabs(hi), fabs(lo)) + 0.5 * fabs(omega) * a.n) * fabs(dt);
+        const double dt = a.dt[s];
+        __syncthreads();
+        if (tid < a.n) {
+            const int q = a.n - 1 - tid;  // index bit tid <-> qubit q
+            const long long row = a.site_stride ? s * a.site_stride + q : s;
+            hw_s[tid] = 0.5 * a.omega[row] * a.w_omega[q] + a.x0[q];
+            d_s[tid] = a.delta[row] * a.w_delta[q];
+        }
+        __syncthreads();
+        double hw_abs = 0.0, d_pos = 0.0, d_neg = 0.0;
+        for (int b = 0; b < a.n; ++b) {
+            hw_abs += fabs(hw_s[b]);
+            d_pos += fmax(d_s[b], 0.0);
+            d_neg += fmax(-d_s[b], 0.0);
+        }
+        const double hi = a.diag_max + d_neg, lo = a.diag_min - d_pos;
+        const double theta = (fmax(fabs(hi), fabs(lo)) + hw_abs) * fabs(dt);
         int nsub = (int)ceil(theta / a.theta_max);
         if (nsub < 1) nsub = 1;
         const double h = dt / nsub, theta_sub = theta / nsub;
@@ -79,10 +97,15 @@ __global__ void __launch_bounds__(kSmallThreads, 1) evolve_small_kernel(const Sm
                 double nrm = 0.0;
                 for (int k = tid; k < dim; k += kSmallThreads) {
                     const double2 xk = x[k];
-                    double2 sum = make_double2(0.0, 0.0);
-                    for (int q = 0; q < a.n; ++q) cacc(sum, x[k ^ (1 << q)]);
-                    const double d = __ldg(a.eint + k) - delta * (double)__popc(k);
-                    double2 v = make_double2(d * xk.x + half_omega * sum.x, d * xk.y + half_omega * sum.y);
+                    double d = __ldg(a.eint + k);
+                    for (int q = 0; q < a.n; ++q)
+                        if ((k >> q) & 1) d -= d_s[q];
+                    double2 v = make_double2(d * xk.x, d * xk.y);
+                    for (int q = 0; q < a.n; ++q) {
+                        const double2 w = x[k ^ (1 << q)];
+                        v.x = fma(hw_s[q], w.x, v.x);
+                        v.y = fma(hw_s[q], w.y, v.y);
+                    }
                     v = cmul(c, v);
                     nrm += cnorm2(v);
                     y[k] = v;
@@ -104,14 +127,21 @@ __global__ void __launch_bounds__(kSmallThreads, 1) evolve_small_kernel(const Sm
         }
         // energy e_ops after the step: <psi|H(omega_e, delta_e)|psi>
         for (int o = 0; o < a.n_eops && !err; ++o) {
-            const double ho = 0.5 * a.eop_omega[o], de = a.eop_delta[o];
+            const double oe = a.eop_omega[o], de = a.eop_delta[o];
             double acc = 0.0;
             for (int k = tid; k < dim; k += kSmallThreads) {
                 const double2 xk = psi[k];
-                double2 sum = make_double2(0.0, 0.0);
-                for (int q = 0; q < a.n; ++q) cacc(sum, psi[k ^ (1 << q)]);
-                const double d = __ldg(a.eint + k) - de * (double)__popc(k);
-                acc += xk.x * (d * xk.x + ho * sum.x) + xk.y * (d * xk.y + ho * sum.y);  // Re conj(psi) (H psi)
+                double d = __ldg(a.eint + k);
+                double2 v = make_double2(0.0, 0.0);
+                for (int b = 0; b < a.n; ++b) {
+                    const int q = a.n - 1 - b;
+                    if ((k >> b) & 1) d -= de * a.w_delta[q];
+                    const double hq = 0.5 * oe * a.w_omega[q] + a.x0[q];
+                    const double2 w = psi[k ^ (1 << b)];
+                    v.x = fma(hq, w.x, v.x);
+                    v.y = fma(hq, w.y, v.y);
+                }
+                acc += xk.x * (d * xk.x + v.x) + xk.y * (d * xk.y + v.y);  // Re conj(psi) (H psi)
             }
             acc = block_allreduce(acc, red, &bcast);
             if (tid == 0) a.expect_out[s * a.n_eops + o] = acc;
