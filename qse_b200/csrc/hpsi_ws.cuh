@@ -47,8 +47,14 @@ namespace qsb {
 constexpr int kConsumerWarps = 16;
 // warps 0..15 consume, warp 16 produces, warps 17..19 only pad the producer to a full warpgroup:
 // registers are allocated per warpgroup, and setmaxnreg moves the producer group's share
-// (96 -> 40 per thread) to the consumers (96 -> 112).
+// (96 -> 32 per thread) to the consumers (96 -> 112).
 constexpr int kWsThreads = (kConsumerWarps + 4) * 32;  // 640
+// setmaxnreg.inc BLOCKS until the CTA's register pool (kWsRegsLaunch per thread at launch) holds what it
+// asks for: the producer group must release at least what the consumers take, or the kernel deadlocks.
+constexpr int kWsRegsLaunch = 96, kWsRegsProducer = 32, kWsRegsConsumer = 112;
+static_assert(4 * (kWsRegsLaunch - kWsRegsProducer) >= kConsumerWarps * (kWsRegsConsumer - kWsRegsLaunch), "setmaxnreg budget");
+#define QSB_STR2(x) #x
+#define QSB_STR(x) QSB_STR2(x)
 constexpr size_t kWsSmemBytes = 192 * 1024;            // the tile ring
 
 // Tile geometry.  A tile holds 2^TB amplitudes; a consumer thread owns 8 of them, so a tile is
@@ -72,7 +78,8 @@ enum { kItemFirst = 0, kItemInner = 1, kItemPlain = 2, kItemDone = 3, kItemPeer 
 
 struct WsItem {
     u64 base;
-    double dhi;  // FIRST: sum of delta_q over the set index bits >= TB of the tile base (+ the rank's bits)
+    double dhi;    // FIRST: diagonal of the tile base (index bits >= TB and the rank's bits): pairs + single-bit terms
+    double w[12];  // FIRST, diagonal on the fly: w[b] = sum over the set high bits h of the base of V(h, b), tile bit b
     int type;
     int sb;
 };
@@ -86,6 +93,16 @@ struct HpsiWs {
     const double2* peer[kMaxPeers];
     int n_peer;
     SiteParams sp;   // per-site Omega_q / 2 and delta_q by index bit (hw_peer = 1.0 with the remap exchange)
+    // Diagonal on the fly (otf = 1): the diagonal of H is 2-local,
+    //     d(k) = c0 + sum_b lin[b] b_b(k) + sum_{b<b'} vbits[b][b'] b_b(k) b_b'(k)       (LOCAL index bits b),
+    // with the rank's bits, the detuning and any static 1- / 2-local diagonal strings folded into c0 and lin
+    // by the host.  A thread's 8 amplitudes keep their tile-index part in 8 registers for the whole launch;
+    // the producer adds the tile-base part per tile: no E array is read (-8 B/amplitude of HBM traffic, no
+    // global load in front of the flip phase).  otf = 0 reads E from eint (3+-local static strings).
+    int otf;
+    const double* vbits;          // [kMaxLocalBits][kMaxLocalBits], symmetric, zero diagonal (device)
+    double lin[kMaxLocalBits];
+    double c0;
     double2 scale;
     int nl;
     int fused;       // 1: fused FIRST+INNER launch over super-blocks; 0: plain launch
@@ -196,14 +213,15 @@ QSB_DEV void cfma(double2& v, double c, double2 x) {
 // FIRST = contiguous tile (index bits 0..TB-1 + diagonal + peers); otherwise strided rows (bits >= lb).
 // A thread owns tile indices idx = t + j * kGroupThreads (j = 0..7): tile bits [TB-3, TB) are
 // register-only flips, every other active tile bit is a conflict-free LDS.128 at an XOR-permuted
-// address.  Global operands (E or partial y, the first NVLink partner) are requested up front with
-// loads the compiler may not sink, so their latency hides behind the shared-memory flip phase.
+// address.  Global operands (the partial y; E when the diagonal is not computed on the fly) are
+// requested up front with loads the compiler may not sink and are CONSUMED LAST, after the
+// shared-memory flip phase, so that their L2 / HBM latency hides behind it.
 // PEER (FIRST only, sharded state): the producer has already pulled the partner tiles over NVLink
 // (kItemPeer stages, ws_peer below) and y holds sum_g hw_g * partner_g.
-// dsum: FIRST only -- sum of delta_q over the set bits of this thread's index t (bits 0..TB-4) plus
-// the tile's high part (WsItem::dhi).
+// diag: FIRST only -- the diagonal of H for this thread's 8 amplitudes.
 template <int TB, bool FIRST, bool PEER, bool LAST>
-QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 base, int t, double dsum, double& red) {
+QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 base, int t, const double (&diag)[kPerThread],
+                        double& red) {
     using C = WsCfg<TB>;
     const int lb = FIRST ? TB : p.lb;
     const int hb0 = FIRST ? TB : p.hb0;
@@ -219,21 +237,14 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
     (FIRST ? (u64)((j)*C::kGroupThreads) : (((((u64)((j)*C::kGroupThreads)) >> lb) << hb0) | (((u64)((j)*C::kGroupThreads)) & low_mask)))
 #define QSB_GADDR(j) (g0 + QSB_GOFF(j))
 
-    double e[FIRST ? kPerThread : 1];
+    constexpr bool kHaveY = !FIRST || PEER;
+    double2 yv[kHaveY ? kPerThread : 1];
     double2 v[kPerThread];
-    if constexpr (FIRST) {
+    // the partial y (non-FIRST; L2-resident: written by the FIRST tiles of this super-block, or prefetched
+    // by the producer) or the partners' term (FIRST + PEER)
+    if constexpr (kHaveY) {
 #pragma unroll
-        for (int j = 0; j < kPerThread; ++j) e[j] = ldnc1(p.eint + QSB_GADDR(j));
-    }
-    // The accumulators START as the partial y (non-FIRST; L2-resident: written by the FIRST tiles of this
-    // super-block, or prefetched by the producer) or as the partners' term (FIRST + PEER): the loads
-    // land directly in v, there is no second copy to keep (or to spill) through the flip phases.
-    if constexpr (!FIRST || PEER) {
-#pragma unroll
-        for (int j = 0; j < kPerThread; ++j) v[j] = ldcg2(p.y + QSB_GADDR(j));
-    } else {
-#pragma unroll
-        for (int j = 0; j < kPerThread; ++j) v[j] = make_double2(0.0, 0.0);
+        for (int j = 0; j < kPerThread; ++j) yv[j] = ldcg2(p.y + QSB_GADDR(j));
     }
     {
         double2 xv[kPerThread];
@@ -245,17 +256,10 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
         for (int b = 0; b < kRegBits; ++b) hr[b] = (C::kRegLo + b >= act_lo) ? p.sp.hw[C::kRegLo + b + gshift] : 0.0;
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) {
-            // the three partner products first, y / zero last: the chain does not wait on the global load
             double2 a = make_double2(hr[0] * xv[j ^ 1].x, hr[0] * xv[j ^ 1].y);
             cfma(a, hr[1], xv[j ^ 2]);
             cfma(a, hr[2], xv[j ^ 4]);
-            if constexpr (FIRST) {
-                // diagonal: d = E - sum_q delta_q b_q(k); bits TB-3..TB-1 of the index are j's bits
-                const double dj = ((j & 1) ? p.sp.dl[C::kRegLo] : 0.0) + ((j & 2) ? p.sp.dl[C::kRegLo + 1] : 0.0) +
-                                  ((j & 4) ? p.sp.dl[C::kRegLo + 2] : 0.0);
-                cfma(a, e[j] - (dsum + dj), xv[j]);
-            }
-            if constexpr (!FIRST || PEER) cacc(a, v[j]);
+            if constexpr (FIRST) cfma(a, diag[j], xv[j]);
             v[j] = a;
         }
     }
@@ -274,6 +278,10 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
 #pragma unroll
             for (int j = 0; j < kPerThread; ++j) cfma(v[j], h, ts[tb + j * C::kGroupThreads]);
         }
+    }
+    if constexpr (kHaveY) {
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) cacc(v[j], yv[j]);
     }
     // output addresses are formed only now (same trick): no 64-bit address lives through the flip phase
     const u64 ge = g0 + ((u64)__double_as_longlong(v[0].x) & p.zero);
@@ -352,10 +360,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
     __shared__ int warps_done[C::kStages];
     __shared__ double red[32];
     __shared__ int is_last_cta;
+    __shared__ double vs[kMaxLocalBits * kMaxLocalBits];  // pair table of the diagonal, LOCAL index bits
 
     const int t = threadIdx.x;
     const int warp = t >> 5, lane = t & 31;
 
+    if (p.fused) {
+        for (int i = t; i < kMaxLocalBits * kMaxLocalBits; i += kWsThreads) vs[i] = p.vbits[i];
+    }
     if (t == 0) {
 #pragma unroll
         for (int s = 0; s < C::kStages; ++s) {
@@ -370,7 +382,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
     double part = 0.0;
     if (warp >= kConsumerWarps) {
         // ================= producer warpgroup (only its first warp works) =================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " QSB_STR(32) ";");  // kWsRegsProducer
         if (warp == kConsumerWarps) {
             // Static schedule from ONE global ticket counter.  Tickets enumerate phases of n_a tiles:
             //   A(0) .. A(L-1),  then  A(s), B(s-L)  for s = L .. n_sb-1,  then  B(n_sb-L) .. B(n_sb-1)
@@ -469,7 +481,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                     constexpr int chunk = C::kTileW / kCopies;
                     if (lane < kCopies)
                         bulk_g2s(stage + lane * chunk, p.x + base + (u64)lane * chunk, chunk * sizeof(double2), &full_bar[s]);
-                    if (lane == kCopies) prefetch_l2(p.eint + base, (uint32_t)(C::kTileW * sizeof(double)));
+                    if (lane == kCopies && !p.otf) prefetch_l2(p.eint + base, (uint32_t)(C::kTileW * sizeof(double)));
                 } else {
                     base = ws_tile_base(p.lb, p.hb, p.hb0, tau);
                     const int rows = 1 << p.hb;
@@ -492,20 +504,31 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                             bulk_g2s(stage + ((size_t)r << p.lb), p.x + base + ((u64)r << p.hb0), row_bytes, &full_bar[s]);
                     }
                 }
-                if (lane == 0) {
-                    double dhi = 0.0;
-                    if (type == kItemFirst) {
-                        // detuning of the index bits above the tile (identical for its 2^TB amplitudes)
-                        dhi = p.sp.d_rank;
-                        for (u64 rest = base >> TB; rest; rest &= rest - 1ull) dhi += p.sp.dl[TB + __ffsll((long long)rest) - 1];
+                if (type == kItemFirst) {
+                    // diagonal of the tile base (identical for its 2^TB amplitudes), while the copies are in
+                    // flight: lane b < TB sums V(h, b) over the set high bits h (the single-bit offset of tile
+                    // bit b); lane l takes high bit l's own terms, c0 + sum lin[h] + sum_{h<h'} V(h, h')
+                    const u64 hi = base >> TB;
+                    double wl = 0.0, eh = 0.0;
+                    if (lane < TB)
+                        for (u64 rest = hi; rest; rest &= rest - 1ull) wl += vs[(TB + __ffsll((long long)rest) - 1) * kMaxLocalBits + lane];
+                    if ((hi >> lane) & 1ull) {
+                        eh = p.lin[TB + lane];
+                        for (u64 rest = hi >> (lane + 1) << (lane + 1); rest; rest &= rest - 1ull)
+                            eh += vs[(TB + lane) * kMaxLocalBits + TB + __ffsll((long long)rest) - 1];
                     }
+                    eh = warp_sum(eh);
+                    if (lane < TB) desc[s].w[lane] = wl;
+                    if (lane == 0) desc[s].dhi = eh + p.c0;
+                    __syncwarp();
+                }
+                if (lane == 0) {
                     if (type == kItemInner) {
                         // the partial y of this super-block must be complete (all its FIRST tiles stored)
                         while (ld_volatile_u64(p.done + sb) < p.done_target) __nanosleep(32);
                         __threadfence();  // acquire side of the done[] handshake
                     }
                     desc[s].base = base;
-                    desc[s].dhi = dhi;
                     desc[s].type = type;
                     desc[s].sb = sb;
                     mbar_arrive(&full_bar[s]);  // release: descriptor (and the INNER dependency) visible to consumers
@@ -515,14 +538,29 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
         }
     } else {
         // ================= consumer warps =================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " QSB_STR(112) ";");  // kWsRegsConsumer
         const int group = warp / C::kGroupWarps;
         const int tg = t - group * C::kGroupThreads;  // thread index within the group
-        // detuning of the index bits this thread's tile index fixes (bits 0..TB-4 of a FIRST tile)
-        double dlow = 0.0;
+        // Diagonal of the amplitudes this thread owns in EVERY contiguous tile, tile-index part: ett = single-bit
+        // terms and pairs among the bits of tg (tile bits 0..TB-4); cross[jb] = single-bit term of register bit jb
+        // (tile bit TB-3+jb) and its pairs with the bits of tg.  Four values per thread for the whole launch.
+        double ett = 0.0, cross[kRegBits] = {0.0, 0.0, 0.0};
+        if (p.fused) {
 #pragma unroll
-        for (int b = 0; b < C::kRegLo; ++b)
-            if ((tg >> b) & 1) dlow += p.sp.dl[b];
+            for (int b = 0; b < C::kRegLo; ++b)
+                if ((tg >> b) & 1) {
+                    ett += p.lin[b];
+                    for (int b2 = b + 1; b2 < C::kRegLo; ++b2)
+                        if ((tg >> b2) & 1) ett += vs[b * kMaxLocalBits + b2];
+                }
+#pragma unroll
+            for (int jb = 0; jb < kRegBits; ++jb) {
+                double c = p.lin[C::kRegLo + jb];
+                for (int b = 0; b < C::kRegLo; ++b)
+                    if ((tg >> b) & 1) c += vs[b * kMaxLocalBits + C::kRegLo + jb];
+                cross[jb] = c;
+            }
+        }
         for (u64 it = (u64)group;; it += C::kGroups) {
             const int s = (int)(it % C::kStages);
             const u64 use = it / C::kStages;
@@ -533,9 +571,31 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
             const int sb = desc[s].sb;
             const double2* ts = tiles + (size_t)s * C::kTileW;
             if (type == kItemFirst) {
-                const double dsum = dlow + desc[s].dhi;
-                if (p.n_peer > 0) ws_process<TB, true, true, false>(p, ts, base, tg, dsum, part);
-                else ws_process<TB, true, false, false>(p, ts, base, tg, dsum, part);
+                // + the tile-base part: its own terms (dhi) and its coupling to this thread's tile bits (w);
+                // the pairs among the three register bits are warp-uniform table reads
+                double eh = desc[s].dhi + ett;
+#pragma unroll
+                for (int b = 0; b < C::kRegLo; ++b)
+                    if ((tg >> b) & 1) eh += desc[s].w[b];
+                const double c0 = cross[0] + desc[s].w[C::kRegLo], c1 = cross[1] + desc[s].w[C::kRegLo + 1],
+                             c2 = cross[2] + desc[s].w[C::kRegLo + 2];
+                const double p01 = vs[C::kRegLo * kMaxLocalBits + C::kRegLo + 1], p02 = vs[C::kRegLo * kMaxLocalBits + C::kRegLo + 2],
+                             p12 = vs[(C::kRegLo + 1) * kMaxLocalBits + C::kRegLo + 2];
+                double diag[kPerThread];
+                diag[0] = eh;
+                diag[1] = eh + c0;
+                diag[2] = eh + c1;
+                diag[3] = diag[1] + (c1 + p01);
+                diag[4] = eh + c2;
+                diag[5] = diag[4] + (c0 + p02);
+                diag[6] = diag[4] + (c1 + p12);
+                diag[7] = diag[6] + (c0 + (p01 + p02));
+                if (!p.otf) {  // a static diagonal that is not 2-local: the pair table is zero and E comes from memory
+#pragma unroll
+                    for (int j = 0; j < kPerThread; ++j) diag[j] += ldnc1(p.eint + base + tg + j * C::kGroupThreads);
+                }
+                if (p.n_peer > 0) ws_process<TB, true, true, false>(p, ts, base, tg, diag, part);
+                else ws_process<TB, true, false, false>(p, ts, base, tg, diag, part);
                 // publish this tile of partial y: warp barrier -> cta-scope release on the shared
                 // counter; the last warp of the group to finish issues ONE gpu-scope fence (cumulative
                 // over the writes it observed through the counter) and bumps the super-block counter.
@@ -552,8 +612,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
             } else if (type == kItemPeer) {
                 ws_peer<TB>(p, ts, base, sb, tg);
             } else {
-                if (p.last) ws_process<TB, false, false, true>(p, ts, base, tg, 0.0, part);
-                else ws_process<TB, false, false, false>(p, ts, base, tg, 0.0, part);
+                const double nodiag[kPerThread] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                if (p.last) ws_process<TB, false, false, true>(p, ts, base, tg, nodiag, part);
+                else ws_process<TB, false, false, false>(p, ts, base, tg, nodiag, part);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);

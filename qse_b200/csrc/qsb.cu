@@ -86,6 +86,13 @@ struct qsb_ctx {
     double gen_bound[3] = {0.0, 0.0, 0.0};  // sum |coef| per channel (spectral bound)
     bool have_terms = false;                // qsb_set_operator_terms was called (E holds their static diagonal)
     std::vector<double> v_host;             // last interaction matrix (E is rebuilt when the terms change)
+    // 2-local model of the static diagonal, by QUBIT: E(k) = dm_c0 + sum_q dm_lin[q] b_q + sum_{q<q'} dm_pair[q][q'] b_q b_q'
+    // (interaction + static diagonal strings of at most two factors); dm_ok = false when a longer string exists
+    bool dm_ok = false;
+    double dm_c0 = 0.0;
+    std::vector<double> dm_lin, dm_pair;
+    double* vbits_dev = nullptr;            // dm_pair over the LOCAL index bits, [kMaxLocalBits][kMaxLocalBits]
+    int diag_otf = 1;                       // option "diag_on_the_fly"
     // options
     double tol = 1e-14, theta_max = 3.0;
     int max_terms = 64, fixed_terms = 0, force_flat = 0;
@@ -294,6 +301,12 @@ struct HParams {
     double hw_abs = 0.0;            // sum_q |hw_q|                      (spectral bound)
     double d_pos = 0.0, d_neg = 0.0;  // sum_q max(delta_q, 0), sum_q max(-delta_q, 0)
     double chan[3] = {1.0, 0.0, 0.0};  // scale of the operator terms of channel 0 (static), 1 (amplitude), 2 (detuning)
+    // diagonal of H over the LOCAL index bits with the rank's bits folded in (hpsi_ws.cuh, "diagonal on the fly"):
+    // d(k) = c0 + sum_b lin[b] b_b(k) + sum_{b<b'} vbits[b][b'] b_b b_b'; with a stored E array the pair table is
+    // zero and (c0, lin) carry only the detuning
+    double lin[kMaxLocalBits];
+    double c0 = 0.0;
+    bool otf = false;
 };
 
 // hw_site[q], d_site[q] for q = 0..n-1 (qubit q <-> index bit n-1-q; bits >= nl are rank bits)
@@ -317,6 +330,32 @@ static HParams hparams_from_sites(const qsb_ctx* c, const double* hw_site, const
     h.chan[0] = 1.0;
     h.chan[1] = amp;
     h.chan[2] = det;
+    // diagonal model: detuning, plus (on the fly) the static 1- / 2-local part with this rank's bits folded in
+    h.otf = c->diag_otf && c->dm_ok;
+    memset(h.lin, 0, sizeof(h.lin));
+    h.c0 = -h.sp.d_rank;
+    for (int b = 0; b < c->nl; ++b) h.lin[b] = -h.sp.dl[b];
+    if (h.otf) {
+        const int n = c->n;
+        h.c0 += c->dm_c0;
+        for (int q = 0; q < n; ++q) {
+            const int bit = n - 1 - q;
+            if (bit < c->nl) {
+                h.lin[bit] += c->dm_lin[q];
+                for (int g = 0; g < c->p; ++g)  // sharded qubit g' = n-1-(nl+g) set in this rank
+                    if ((c->rank >> g) & 1) {
+                        const int qg = n - 1 - (c->nl + g);
+                        h.lin[bit] += c->dm_pair[(size_t)std::min(q, qg) * n + std::max(q, qg)];
+                    }
+            } else if ((c->rank >> (bit - c->nl)) & 1) {
+                h.c0 += c->dm_lin[q];
+                for (int q2 = q + 1; q2 < n; ++q2) {
+                    const int bit2 = n - 1 - q2;
+                    if (bit2 >= c->nl && ((c->rank >> (bit2 - c->nl)) & 1)) h.c0 += c->dm_pair[(size_t)q * n + q2];
+                }
+            }
+        }
+    }
     return h;
 }
 // the global pulse of qse.calc.Qutip (qse/calc/qutip.py:55-58) through the per-site weights
@@ -355,6 +394,10 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, const HParam
     const int grid = (int)std::min<u64>(n_tiles, (u64)c->n_sm);
     HpsiWs a{};
     a.sp = hp.sp;
+    a.otf = hp.otf ? 1 : 0;
+    a.vbits = c->vbits_dev + (hp.otf ? 0 : kMaxLocalBits * kMaxLocalBits);  // second table: all zero
+    memcpy(a.lin, hp.lin, sizeof(a.lin));
+    a.c0 = hp.c0;
     // remap exchange: from 4 ranks up, when peer memory is mapped and a chunk holds whole tiles
     const bool remap = c->nranks >= 4 && c->nranks <= 8 && c->ipc && c->zbuf && c->exchange != 0 && (c->nl - c->p) >= w.tb;
     if (remap) {
@@ -1129,6 +1172,7 @@ int qsb_destroy(qsb_ctx* c) {
     cudaFree(c->topk_buf);
     cudaFree(c->tickets);
     cudaFree(c->gen_dev);
+    cudaFree(c->vbits_dev);
     cudaFree(c->diag_dev);
     cudaFree(c->sched_dev);
     cudaFree(c->sb_done);
@@ -1184,6 +1228,8 @@ int qsb_set_option(qsb_ctx* c, const char* key, double value) {
     } else if (!strcmp(key, "exchange")) {
         if (value != -1.0 && value != 0.0 && value != 1.0) return fail(c, QSB_ERR_INVALID, "exchange must be -1, 0 or 1");
         c->exchange = (int)value;
+    } else if (!strcmp(key, "diag_on_the_fly")) {
+        c->diag_otf = value != 0.0;
     } else if (!strcmp(key, "small_kernel")) {
         c->small_kernel = value != 0.0;
     } else if (!strcmp(key, "tensor_map")) {
@@ -1204,9 +1250,78 @@ int qsb_set_option(qsb_ctx* c, const char* key, double value) {
     return QSB_OK;
 }
 
+// The static diagonal as a 2-local polynomial in the occupation bits (Z = 1 - 2 n): what the H psi kernel
+// evaluates on the fly instead of reading E.  Strings of three or more factors do not fit (dm_ok = false).
+static int build_diag_model(qsb_ctx* c) {
+    const int n = c->n;
+    c->dm_c0 = 0.0;
+    c->dm_lin.assign((size_t)n, 0.0);
+    c->dm_pair.assign((size_t)n * n, 0.0);
+    c->dm_ok = true;
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j) c->dm_pair[(size_t)i * n + j] = c->v_host[(size_t)i * n + j];
+    for (const DiagTerm& g : c->diag_terms) {
+        int q[2], isz[2], k = 0;
+        bool fits = true;
+        for (int bit = 0; bit < n; ++bit) {
+            const bool z = (g.z >> bit) & 1ull, nn = (g.nm >> bit) & 1ull;
+            if (!z && !nn) continue;
+            if (k == 2) {
+                fits = false;
+                break;
+            }
+            q[k] = n - 1 - bit;
+            isz[k] = z ? 1 : 0;
+            ++k;
+        }
+        if (!fits) {
+            c->dm_ok = false;
+            continue;
+        }
+        if (k == 0) {
+            c->dm_c0 += g.coef;
+        } else if (k == 1) {
+            if (isz[0]) {
+                c->dm_c0 += g.coef;
+                c->dm_lin[q[0]] -= 2.0 * g.coef;
+            } else {
+                c->dm_lin[q[0]] += g.coef;
+            }
+        } else {
+            const int a = std::min(q[0], q[1]), b = std::max(q[0], q[1]);
+            double& pr = c->dm_pair[(size_t)a * n + b];
+            if (isz[0] && isz[1]) {  // (1 - 2 n_a)(1 - 2 n_b)
+                c->dm_c0 += g.coef;
+                c->dm_lin[q[0]] -= 2.0 * g.coef;
+                c->dm_lin[q[1]] -= 2.0 * g.coef;
+                pr += 4.0 * g.coef;
+            } else if (!isz[0] && !isz[1]) {
+                pr += g.coef;
+            } else {  // Z_z n_m = n_m - 2 n_z n_m
+                const int m = isz[0] ? q[1] : q[0];
+                c->dm_lin[m] += g.coef;
+                pr -= 2.0 * g.coef;
+            }
+        }
+    }
+    // pair table over the LOCAL index bits (+ an all-zero copy for the stored-E mode), symmetric
+    std::vector<double> tab(2 * (size_t)kMaxLocalBits * kMaxLocalBits, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j) {
+            const int bi = n - 1 - i, bj = n - 1 - j;
+            if (bi >= c->nl || bj >= c->nl) continue;
+            tab[(size_t)bi * kMaxLocalBits + bj] = tab[(size_t)bj * kMaxLocalBits + bi] = c->dm_pair[(size_t)i * n + j];
+        }
+    if (!c->vbits_dev) CU(cudaMalloc(&c->vbits_dev, tab.size() * sizeof(double)));
+    CU(cudaMemcpyAsync(c->vbits_dev, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));  // tab is a local
+    return QSB_OK;
+}
+
 // E <- interaction diagonal (K1) + static diagonal operator strings; refresh its range
 static int rebuild_diagonal(qsb_ctx* c) {
     const int n = c->n;
+    TRY(build_diag_model(c));
     CU(cudaMemcpyAsync(c->vtab, c->v_host.data(), c->v_host.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     const int grid = grid_for(c, c->dim, 256);
     diag_build_kernel<<<grid, 256, (size_t)n * n * sizeof(double), c->stream>>>(c->eint, c->vtab, n, c->nl, c->rank_bits);

@@ -22,6 +22,89 @@ from qse_b200 import distributed as qdist  # noqa: E402
 from qse_b200 import lib  # noqa: E402
 
 
+def large_shard_cases(rank, world, local, check):
+    """The shard sizes bench.py / SCALE run (2^25 amplitudes per GPU: 26 qubits on 2, 27 on 4, 28 on 8
+    GPUs), against the oracle's C port: plain launch + fused Taylor epilogue + (from 4 ranks) the remap
+    exchange with its staggered super-block order -- none of which the small cases reach.  Also the
+    direct exchange at the same size and a sharded checkpoint round trip."""
+    import tempfile
+
+    import bench
+    from oracle import c_port
+
+    p = world.bit_length() - 1
+    n = int(os.environ.get("QSB_WORKER_LARGE_QUBITS", 25 + p))
+    nl = n - p
+    qbits, amp, det = bench.workload(n, 23)
+    om, de, dt = qb.flatten_schedule(qb.Signals([amp]), qb.Signals([det]))
+    sel = slice(10, 12)
+
+    def shard(r):
+        rng = np.random.default_rng(9000 + 16 * n + r)
+        return (rng.standard_normal(1 << nl) + 1j * rng.standard_normal(1 << nl)) / np.sqrt(2.0 ** (n + 1))
+
+    mine = shard(rank)
+    uid = qdist.broadcast_unique_id()
+    eng = lib.Engine(n, device=local, rank=rank, nranks=world, nccl_uid=uid)
+    eng.set_interaction(qb.interaction_matrix(qbits.positions))
+    eng.set_state(mine)
+    y = {"default": eng.apply_h(om[11], de[11])}
+    if world >= 4:
+        eng.set_option("exchange", 0)
+        y["direct"] = eng.apply_h(om[11], de[11])
+        eng.set_option("exchange", -1)
+    eng.evolve_schedule(om[sel], de[sel], dt[sel])
+    evolved = eng.get_state()
+    spins = eng.spins()
+    # rank 0 holds the reference: the same shards, the C port on the host cores
+    full_y = {k: qdist.gather_shards(v) for k, v in y.items()}
+    full_e = qdist.gather_shards(evolved)
+    diag = qdist.gather_shards(eng.diagonal().astype(np.complex128)).real
+    if rank == 0:
+        psi = np.concatenate([shard(r) for r in range(world)])
+        v = orc.interaction_matrix(qbits.positions)
+        e = c_port.build_diagonal(v, n)
+        c_port.set_threads(os.cpu_count() or 1)
+        check(f"large n={n} diagonal bit-exact", np.array_equal(diag, e))
+        want_h = c_port.apply_h(psi, e, n, om[11], de[11])
+        for k, got in full_y.items():
+            err = float(np.max(np.abs(got - want_h)) / np.max(np.abs(want_h)))
+            check(f"large n={n} H psi ({k} exchange) vs C port", err <= 1e-13, f"rel err {err:.2e}")
+        want, _ = c_port.evolve_schedule(psi, e, n, om[sel], de[sel], dt[sel])
+        nrm = float(np.vdot(psi, psi).real)
+        infid = orc.infidelity(full_e / np.sqrt(nrm), want / np.sqrt(nrm))
+        check(f"large n={n} 2-step sweep infidelity vs C port", infid <= 1e-10, f"{infid:.2e}")
+        dmax = float(np.max(np.abs(full_e - want)))
+        check(f"large n={n} 2-step sweep state", dmax <= 1e-9, f"{dmax:.2e}")
+        d = float(np.max(np.abs(spins - c_port.spins(want, n))))
+        check(f"large n={n} spins after the sweep", d <= 1e-9, f"{d:.2e}")
+    eng.close()
+    # sharded checkpoint: stop after 2 of 4 values, save, resume in a new calculator, compare with one go
+    tmp = [tempfile.mkdtemp(prefix="qsb_ckpt_") if rank == 0 else None]
+    dist.broadcast_object_list(tmp, src=0)
+    prefix = os.path.join(tmp[0], "sweep")
+    a4, d4 = qb.Signal(amp.values[10:14], 4), qb.Signal(det.values[10:14], 4)
+    calc = qb.B200(qbits, a4, d4, return_state=False, compute_spins=False)
+    calc.calculate()
+    whole = calc._engine.get_state().copy()
+    calc.calculate(stop_after=2)
+    calc.save_checkpoint(prefix, 2)
+    calc.close()
+    dist.barrier()
+    calc = qb.B200(qbits, a4, d4, return_state=False, compute_spins=False)
+    calc.calculate(resume_from=prefix)
+    resumed = calc._engine.get_state()
+    ok = torch.tensor([1.0 if np.array_equal(resumed, whole) else 0.0], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    check(f"large n={n} sharded checkpoint resume is bit-identical", ok.item() == 1.0)
+    calc.close()
+    dist.barrier()
+    if rank == 0:
+        import shutil
+
+        shutil.rmtree(tmp[0], ignore_errors=True)
+
+
 def main():
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
@@ -96,7 +179,7 @@ def main():
             t = 8
             amp = qb.Signal(np.linspace(0, omega_max, t), 4 * t)
             det = qb.Signal(np.linspace(-2 * omega_max, 2 * omega_max, t), 4 * t)
-            calc = qb.B200(reg, amp, det, compute_spins=(exchange == "ipc"))
+            calc = qb.B200(reg, amp, det)  # default arguments: spins are reduced on the device in both exchange modes
             h_f = calc.get_hamiltonian(omega_max, 2 * omega_max)
             out = calc.calculate(e_ops=[h_f])
             method = "eigh" if n <= 10 else "expm_multiply"
@@ -108,10 +191,12 @@ def main():
             check(f"{exchange} n={n} sweep state", dmax <= 1e-9, f"{dmax:.2e}")
             dexp = float(np.max(np.abs(out["expectations"] - ref["expectations"])))
             check(f"{exchange} n={n} expectations", dexp <= 1e-9 * max(1.0, float(np.max(np.abs(ref["expectations"])))), f"{dexp:.2e}")
-            if exchange == "ipc":
-                d = float(np.max(np.abs(calc.spins - orc.get_spins(ref["state"], n))))
-                check(f"n={n} sweep spins", d <= 1e-9, f"{d:.2e}")
+            d = float(np.max(np.abs(calc.spins - orc.get_spins(ref["state"], n))))
+            check(f"{exchange} n={n} sweep spins", d <= 1e-9, f"{d:.2e}")
             calc.close()
+    os.environ.pop("QSB_NO_IPC", None)
+    if os.environ.get("QSB_WORKER_LARGE", "1") != "0":
+        large_shard_cases(rank, world, local, check)
     t = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(t)
     dist.destroy_process_group()

@@ -4,6 +4,8 @@ BASELINE.json's full sizes — through size-independent properties.
 
 Tolerances (BASELINE.json north_star): final-state infidelity <= 1e-10, observables <= 1e-9
 absolute (complex128), diagonal / basis indexing bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -385,6 +387,41 @@ def test_full_size_25_qubits_properties():
             eng.set_state(psi)
             outs.append(eng.apply_h(OMEGA_MAX, -1.5))
     assert np.max(np.abs(outs[0] - outs[1])) <= 1e-13 * np.max(np.abs(outs[1]))
+
+
+def test_bench_workload_25_qubits_vs_c_port():
+    """The exact workload bench.py times (BASELINE config 2: square 5x5, 25 qubits, adiabatic ramp at
+    1 ns per value) against the oracle's C port at full size: H psi on a random state, then three
+    mid-ramp sweep steps from that state -- infidelity <= 1e-10, max |delta psi| <= 1e-9 (phase
+    included), spins <= 1e-9.  qse/calc/qutip.py:34-53."""
+    import bench
+    from oracle import c_port
+
+    n = 25
+    qbits, amp, det = bench.workload(n, 23)
+    om, de, dt = qb.flatten_schedule(qb.Signals([amp]), qb.Signals([det]))
+    v = orc.interaction_matrix(qbits.positions)
+    e = c_port.build_diagonal(v, n)
+    rng = np.random.default_rng(2025)
+    psi = (rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)) / np.sqrt(2.0 ** (n + 1))
+    psi /= np.linalg.norm(psi)
+    c_port.set_threads(os.cpu_count() or 1)
+    sel = slice(10, 13)  # mid-ramp: Omega ~ 2.9..3.4, delta ~ -1.1..+1.1
+    want_h = c_port.apply_h(psi, e, n, om[12], de[12])
+    want, n_hpsi = c_port.evolve_schedule(psi, e, n, om[sel], de[sel], dt[sel])
+    with lib.Engine(n) as eng:
+        eng.set_interaction(qb.interaction_matrix(qbits.positions))
+        assert np.array_equal(eng.diagonal(), e)  # the 256 MiB diagonal, bit for bit
+        eng.set_state(psi)
+        got_h = eng.apply_h(om[12], de[12])
+        assert np.max(np.abs(got_h - want_h)) <= 1e-13 * np.max(np.abs(want_h))
+        eng.evolve_schedule(om[sel], de[sel], dt[sel])
+        got = eng.get_state()
+        spins = eng.spins()
+    assert orc.infidelity(got, want) <= INFID_TOL
+    assert np.max(np.abs(got - want)) <= OBS_TOL
+    assert np.max(np.abs(spins - c_port.spins(want, n))) <= OBS_TOL
+    assert n_hpsi >= 3
 
 
 # ---- BASELINE configs 3 and 5 at full size: size-independent properties --------------------------
