@@ -73,6 +73,12 @@ struct WsCfg {
     static_assert(kGroups >= 1 && kStages >= 2 && kStages <= 12, "tile size");
 };
 constexpr int kMaxStages = 12;
+constexpr int kPubSlots = 8;
+#ifdef QSB_NO_PUBLISHER
+constexpr bool kPublisher = false;
+#else
+constexpr bool kPublisher = true;
+#endif
 
 enum { kItemFirst = 0, kItemInner = 1, kItemPlain = 2, kItemDone = 3, kItemPeer = 4 };
 
@@ -119,6 +125,7 @@ struct HpsiWs {
     unsigned long long* done;   // per super-block: FIRST tiles completed (cumulative over launches)
     unsigned long long done_target;
     u64 n_tiles;     // tiles per sub-pass (= dim >> TB)
+    int tk_batch;    // tickets claimed per atomic (>= 1)
     int use_tmap;    // strided tiles are fetched with ONE 2-D tensor-map TMA per <= 256 rows
     u64 zero;        // always 0, but only the host knows: (bits & zero) makes an address DEPEND on a value, which
                      // pins a load after the phase that produced the value whatever ptxas would like to hoist
@@ -221,7 +228,7 @@ QSB_DEV void cfma(double2& v, double c, double2 x) {
 // diag: FIRST only -- the diagonal of H for this thread's 8 amplitudes.
 template <int TB, bool FIRST, bool PEER, bool LAST>
 QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 base, int t, const double (&diag)[kPerThread],
-                        double& red) {
+                        double& red, uint64_t* empty) {
     using C = WsCfg<TB>;
     const int lb = FIRST ? TB : p.lb;
     const int hb0 = FIRST ? TB : p.hb0;
@@ -279,6 +286,11 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
             for (int j = 0; j < kPerThread; ++j) cfma(v[j], h, ts[tb + j * C::kGroupThreads]);
         }
     }
+    if constexpr (!LAST) {
+        // the tile has been read for the last time: hand the stage back to the producer before the stores
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(empty);
+    }
     if constexpr (kHaveY) {
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) cacc(v[j], yv[j]);
@@ -322,6 +334,8 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
                 p.y[g] = o;
             }
         }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(empty);
     }
 #undef QSB_GADDR
 #undef QSB_GOFF
@@ -357,7 +371,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
     __shared__ __align__(8) uint64_t full_bar[C::kStages];
     __shared__ __align__(8) uint64_t empty_bar[C::kStages];
     __shared__ WsItem desc[C::kStages];
-    __shared__ int warps_done[C::kStages];
+    __shared__ int warps_done[2 * C::kStages];  // by item, not by stage: a stage is released before its tile is published
+    // one consumer group: a PUBLISHER warp (one of the producer group's spare warps) turns "all 16 warps have
+    // stored their part of a FIRST tile" into the gpu-scope fence + done[] increment, so that no consumer warp
+    // ever sits in a membar waiting for its stores to drain
+    __shared__ __align__(8) uint64_t pub_bar[kPubSlots];
+    __shared__ int pub_sb[kPubSlots];
+    __shared__ int pub_seq;
     __shared__ double red[32];
     __shared__ int is_last_cta;
     __shared__ double vs[kMaxLocalBits * kMaxLocalBits];  // pair table of the diagonal, LOCAL index bits
@@ -373,8 +393,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
         for (int s = 0; s < C::kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], C::kGroupWarps);
-            warps_done[s] = 0;
+            warps_done[s] = warps_done[s + C::kStages] = 0;
         }
+        for (int q = 0; q < kPubSlots; ++q) mbar_init(&pub_bar[q], kConsumerWarps);
+        pub_seq = 0;
         mbar_fence_init();
     }
     __syncthreads();
@@ -400,30 +422,45 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
             int peer_left = 0;         // partner stages still to publish for the pending FIRST tile
             bool first_pending = false;
             u64 pend_tau = 0;
+            // Tickets are claimed in batches of p.tk_batch with ONE atomic, and the claim of the NEXT batch is
+            // issued when a batch starts: its round trip (~1 us with every SM on the same counter) hides behind
+            // the batch instead of sitting in front of every tile.  Every CTA makes (useful batches + 1) claims,
+            // so the counter ends at a known value and is never reset (ticket_base).  Batches keep the scheme
+            // deadlock-free: a CTA works through its tickets in increasing order, so the lowest unfinished
+            // ticket of the launch is never stuck behind a higher one.
+            const unsigned int tkb = (unsigned int)p.tk_batch;
+            unsigned int pf = 0;
+            if (lane == 0) pf = atomicAdd(p.ticket, tkb) - p.ticket_base;
+            u64 cur = 0;
+            int left = 0;
             for (u64 it = 0;; ++it) {
                 const int s = (int)(it % C::kStages);
                 const u64 use = it / C::kStages;
-                if (use > 0) mbar_wait(&empty_bar[s], (uint32_t)((use - 1) & 1ull));
                 int type = kItemDone;
                 u64 tau = 0;
                 if (peer_left > 0 || first_pending) {
                     type = peer_left > 0 ? kItemPeer : kItemFirst;
                     tau = pend_tau;
                 } else {
-                    if (lane == 0 && n_done == 0) {
+                    if (n_done == 0 && left == 0) {
                         // the counter is never reset: this launch's tickets start at ticket_base (mod 2^32)
-                        const u64 ticket = (u64)(unsigned int)(atomicAdd(p.ticket, 1u) - p.ticket_base);
-                        if (ticket < total) {
-                            if (!p.fused) {
-                                type = kItemPlain;
-                                tau = ticket;
-                            } else {
-                                type = ws_decode_ticket(ticket, n_a, n_sb, lag, (u64)p.sb_xor, &tau);
-                            }
+                        const u64 b = (u64)__shfl_sync(0xffffffffu, pf, 0);
+                        if (b < total) {
+                            cur = b;
+                            left = (int)((total - b < (u64)tkb) ? (total - b) : (u64)tkb);
+                            if (lane == 0) pf = atomicAdd(p.ticket, tkb) - p.ticket_base;
                         }
                     }
-                    type = __shfl_sync(0xffffffffu, type, 0);
-                    tau = __shfl_sync(0xffffffffu, tau, 0);
+                    if (left > 0) {
+                        const u64 ticket = cur++;
+                        --left;
+                        if (!p.fused) {
+                            type = kItemPlain;
+                            tau = ticket;
+                        } else {
+                            type = ws_decode_ticket(ticket, n_a, n_sb, lag, (u64)p.sb_xor, &tau);
+                        }
+                    }
                     if (type == kItemFirst && p.n_peer > 0) {
                         // sharded state: the partner tiles go first, one stage each, then the tile itself
                         pend_tau = tau;
@@ -432,6 +469,22 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                         type = kItemPeer;
                     }
                 }
+                // diagonal of a contiguous tile's base (identical for its 2^TB amplitudes), computed while the
+                // stage is still busy: lane b < TB sums V(h, b) over the set high bits h (the single-bit offset of
+                // tile bit b); lane l takes high bit l's own terms, c0 + sum lin[h] + sum_{h<h'} V(h, h')
+                double wl = 0.0, eh = 0.0;
+                if (type == kItemFirst) {
+                    const u64 hi = tau;  // base >> TB
+                    if (lane < TB)
+                        for (u64 rest = hi; rest; rest &= rest - 1ull) wl += vs[(TB + __ffsll((long long)rest) - 1) * kMaxLocalBits + lane];
+                    if ((hi >> lane) & 1ull) {
+                        eh = p.lin[TB + lane];
+                        for (u64 rest = hi >> (lane + 1) << (lane + 1); rest; rest &= rest - 1ull)
+                            eh += vs[(TB + lane) * kMaxLocalBits + TB + __ffsll((long long)rest) - 1];
+                    }
+                    eh = warp_sum(eh);
+                }
+                if (use > 0) mbar_wait(&empty_bar[s], (uint32_t)((use - 1) & 1ull));
                 if (type == kItemPeer) {
                     const int q = p.n_peer - peer_left;
                     --peer_left;
@@ -505,19 +558,6 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                     }
                 }
                 if (type == kItemFirst) {
-                    // diagonal of the tile base (identical for its 2^TB amplitudes), while the copies are in
-                    // flight: lane b < TB sums V(h, b) over the set high bits h (the single-bit offset of tile
-                    // bit b); lane l takes high bit l's own terms, c0 + sum lin[h] + sum_{h<h'} V(h, h')
-                    const u64 hi = base >> TB;
-                    double wl = 0.0, eh = 0.0;
-                    if (lane < TB)
-                        for (u64 rest = hi; rest; rest &= rest - 1ull) wl += vs[(TB + __ffsll((long long)rest) - 1) * kMaxLocalBits + lane];
-                    if ((hi >> lane) & 1ull) {
-                        eh = p.lin[TB + lane];
-                        for (u64 rest = hi >> (lane + 1) << (lane + 1); rest; rest &= rest - 1ull)
-                            eh += vs[(TB + lane) * kMaxLocalBits + TB + __ffsll((long long)rest) - 1];
-                    }
-                    eh = warp_sum(eh);
                     if (lane < TB) desc[s].w[lane] = wl;
                     if (lane == 0) desc[s].dhi = eh + p.c0;
                     __syncwarp();
@@ -525,8 +565,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                 if (lane == 0) {
                     if (type == kItemInner) {
                         // the partial y of this super-block must be complete (all its FIRST tiles stored)
-                        while (ld_volatile_u64(p.done + sb) < p.done_target) __nanosleep(32);
-                        __threadfence();  // acquire side of the done[] handshake
+                        while (ld_acquire_u64(p.done + sb) < p.done_target) __nanosleep(32);  // acquire side of done[]
                     }
                     desc[s].base = base;
                     desc[s].type = type;
@@ -534,6 +573,17 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                     mbar_arrive(&full_bar[s]);  // release: descriptor (and the INNER dependency) visible to consumers
                 }
                 __syncwarp();
+            }
+        } else if (kPublisher && C::kGroups == 1 && warp == kConsumerWarps + 1 && lane == 0 && p.fused) {
+            // ================= publisher (one thread) =================
+            for (unsigned int q = 0;; ++q) {
+                const int slot = (int)(q % kPubSlots);
+                mbar_wait(&pub_bar[slot], (q / kPubSlots) & 1u);  // acquire: all 16 warps have issued their stores
+                const int sb = pub_sb[slot];
+                if (sb < 0) break;
+                __threadfence();  // cumulative gpu-scope release of the tile's stores
+                atomicAdd(p.done + sb, 1ull);
+                *(volatile int*)&pub_seq = (int)(q + 1);
             }
         }
     } else {
@@ -561,12 +611,23 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                 cross[jb] = c;
             }
         }
+        unsigned int n_first = 0;  // contiguous tiles this CTA has processed (publisher sequence number)
         for (u64 it = (u64)group;; it += C::kGroups) {
             const int s = (int)(it % C::kStages);
             const u64 use = it / C::kStages;
             mbar_wait(&full_bar[s], (uint32_t)(use & 1ull));
             const int type = desc[s].type;
-            if (type == kItemDone) break;
+            if (type == kItemDone) {
+                if (kPublisher && C::kGroups == 1 && p.fused && lane == 0) {  // tell the publisher to stop
+                    const int slot = (int)(n_first % kPubSlots);
+                    if (warp == 0) {
+                        while ((int)n_first - *(volatile int*)&pub_seq >= kPubSlots) __nanosleep(20);
+                        pub_sb[slot] = -1;
+                    }
+                    mbar_arrive(&pub_bar[slot]);
+                }
+                break;
+            }
             const u64 base = desc[s].base;
             const int sb = desc[s].sb;
             const double2* ts = tiles + (size_t)s * C::kTileW;
@@ -594,30 +655,43 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
 #pragma unroll
                     for (int j = 0; j < kPerThread; ++j) diag[j] += ldnc1(p.eint + base + tg + j * C::kGroupThreads);
                 }
-                if (p.n_peer > 0) ws_process<TB, true, true, false>(p, ts, base, tg, diag, part);
-                else ws_process<TB, true, false, false>(p, ts, base, tg, diag, part);
+                if (p.n_peer > 0) ws_process<TB, true, true, false>(p, ts, base, tg, diag, part, &empty_bar[s]);
+                else ws_process<TB, true, false, false>(p, ts, base, tg, diag, part, &empty_bar[s]);
                 // publish this tile of partial y: warp barrier -> cta-scope release on the shared
                 // counter; the last warp of the group to finish issues ONE gpu-scope fence (cumulative
                 // over the writes it observed through the counter) and bumps the super-block counter.
                 __syncwarp();
-                if (lane == 0) {
+                if constexpr (kPublisher && C::kGroups == 1) {
+                    if (lane == 0) {
+                        const int slot = (int)(n_first % kPubSlots);
+                        if (warp == 0) {
+                            // the slot's previous use must have been published (the publisher is never that far behind)
+                            while ((int)n_first - *(volatile int*)&pub_seq >= kPubSlots) __nanosleep(20);
+                            pub_sb[slot] = sb;
+                        }
+                        mbar_arrive(&pub_bar[slot]);  // release: this warp's stores precede the publisher's fence
+                    }
+                    ++n_first;
+                } else if (lane == 0) {
                     __threadfence_block();
-                    const int c = atomicAdd(&warps_done[s], 1);
+                    // a warp cannot run more than kStages items ahead of the slowest one: 2 * kStages slots never alias
+                    const int slot = (int)(it % (2 * C::kStages));
+                    const int c = atomicAdd(&warps_done[slot], 1);
                     if (c == C::kGroupWarps - 1) {
-                        warps_done[s] = 0;
+                        warps_done[slot] = 0;
                         __threadfence();
                         atomicAdd(p.done + sb, 1ull);
                     }
                 }
             } else if (type == kItemPeer) {
                 ws_peer<TB>(p, ts, base, sb, tg);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
             } else {
                 const double nodiag[kPerThread] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                if (p.last) ws_process<TB, false, false, true>(p, ts, base, tg, nodiag, part);
-                else ws_process<TB, false, false, false>(p, ts, base, tg, nodiag, part);
+                if (p.last) ws_process<TB, false, false, true>(p, ts, base, tg, nodiag, part, &empty_bar[s]);
+                else ws_process<TB, false, false, false>(p, ts, base, tg, nodiag, part, &empty_bar[s]);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);
         }
     }
     if (p.norm_part == nullptr) return;  // uniform: only the launch that finishes a fused H psi reduces

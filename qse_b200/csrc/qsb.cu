@@ -54,6 +54,7 @@ struct qsb_ctx {
     // warp-specialised super-block path (hpsi_ws.cuh)
     int path = 0;       // 0 auto (ws when N_local >= 13), 1 untiled, 2 one launch per tile-bit group
     int sb_lag = 0;     // lead of the FIRST tiles over the INNER tiles of the fused launch, in super-blocks
+    int tk_batch = 0;   // option "ticket_batch": work items claimed per atomic (0 = auto)
     int ws_tile_bits = 12;  // 12 (64 KiB tiles, 3 stages; measured best) or 11 (32 KiB tiles, 6 stages, two groups); 0 = fewest launches
     int sb_bits = 0;   // log2 of the L2-resident super-block (10 MiB each; 18 / lead 3 measured best on B200)
     unsigned int* tickets = nullptr;        // one work counter per launch of an H psi (never reset: see ticket_base)
@@ -377,10 +378,17 @@ static HParams hparams_rows(const qsb_ctx* c, const double* omega_q, const doubl
     return hparams_from_sites(c, hw, d, amp, det);
 }
 
-static unsigned int take_tickets(qsb_ctx* c, int counter, u64 total, int grid) {
-    // every launch performs exactly total + grid atomicAdds on its counter (one over-the-end ticket per CTA)
+// Work items per claim.  Measured (tools/ab_opts.py, 25 / 28 qubits): batches WIDEN the window of super-blocks in
+// flight (148 CTAs x batch tickets) beyond what the L2 holds and what the A -> B lead covers -- 0.70 / 0.74 /
+// 0.94 / 1.24 ms for batches of 1 / 2 / 4 / 8.  One ticket per claim; the claim of the next ticket is issued
+// when the current one is taken, which hides the round trip just as well.
+static int auto_ticket_batch(u64, int) { return 1; }
+static unsigned int take_tickets(qsb_ctx* c, int counter, u64 total, int grid, int batch) {
+    // every launch advances its counter by exactly batch * (ceil(total / batch) + grid): the useful claims plus
+    // one over-the-end claim per CTA (hpsi_ws.cuh, producer warp)
     const unsigned int base = c->ticket_base[counter];
-    c->ticket_base[counter] = (unsigned int)(base + (unsigned int)total + (unsigned int)grid);
+    const u64 claims = (total + (u64)batch - 1) / (u64)batch + (u64)grid;
+    c->ticket_base[counter] = (unsigned int)(base + (unsigned int)(claims * (u64)batch));
     return base;
 }
 
@@ -444,6 +452,7 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, const HParam
         a.hb0 = g.hb0;
         a.last = (last && fuse) ? 1 : 0;
         a.lag = c->sb_lag > 0 ? c->sb_lag : auto_sb_lag(w.sbits);
+
         a.acc_mode = (fuse && last) ? acc_mode : kAccNone;
         a.red_mode = red_mode;
         a.acc = (a.acc_mode != kAccNone) ? c->psi : nullptr;
@@ -452,7 +461,11 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, const HParam
         a.red_out = reduce ? red_slot : nullptr;
         a.tail = c->tail;
         a.ticket = c->tickets + i;
-        a.ticket_base = take_tickets(c, i, a.fused ? 2 * n_tiles : n_tiles, grid);
+        {
+            const u64 total = a.fused ? 2 * n_tiles : n_tiles;
+            a.tk_batch = c->tk_batch > 0 ? c->tk_batch : auto_ticket_batch(total, grid);
+            a.ticket_base = take_tickets(c, i, total, grid, a.tk_batch);
+        }
         if (i == 0) {
             if (c->ws_sbits_active != w.sbits * 16 + w.tb) {
                 // the counters are cumulative per super-block: a new block size starts a new count
@@ -1228,6 +1241,9 @@ int qsb_set_option(qsb_ctx* c, const char* key, double value) {
     } else if (!strcmp(key, "exchange")) {
         if (value != -1.0 && value != 0.0 && value != 1.0) return fail(c, QSB_ERR_INVALID, "exchange must be -1, 0 or 1");
         c->exchange = (int)value;
+    } else if (!strcmp(key, "ticket_batch")) {
+        if (value < 0 || value > 64) return fail(c, QSB_ERR_INVALID, "ticket_batch must be 0 (auto) or in 1..64");
+        c->tk_batch = (int)value;
     } else if (!strcmp(key, "diag_on_the_fly")) {
         c->diag_otf = value != 0.0;
     } else if (!strcmp(key, "small_kernel")) {
