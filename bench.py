@@ -48,6 +48,16 @@ def workload(n_qubits: int, n_values: int):
     return qbits, amp, det
 
 
+def make_config(n: int, world: int) -> dict:
+    """The workload description both arms print (identical keys and values: the driver compares them)."""
+    p = world.bit_length() - 1
+    return {"workload": f"square {SHAPES[n][0]}x{SHAPES[n][1]} ({n} qubits) adiabatic sweep, complex128, 1 ns steps",
+            "qubits": n, "amplitudes_per_gpu": 1 << (n - p),
+            "l2": "inputs larger than L2 (state 512 MiB per 2^25-amplitude shard vs 126 MB L2); no flush",
+            "parallelism": f"state sharded by top {p} qubit(s) over {world} GPU(s) (the CPU arm runs the whole register on the host)",
+            "stepper": "taylor tol 1e-14"}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -174,13 +184,143 @@ def run_reference(args, rank: int, world: int):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
         "steps_per_s": sps,
-        "config": {"workload": f"square {SHAPES[n][0]}x{SHAPES[n][1]} ({n} qubits) adiabatic sweep, complex128, 1 ns steps",
-                   "arm": "CPU port of the reference path (oracle/c/rydberg_ref.c, OpenMP): QuTiP is not installable here"},
+        "config": make_config(n, world),
+        "arm": "CPU port of the reference path (oracle/c/rydberg_ref.c, OpenMP): QuTiP is not installable here",
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+# --------------------------------------------------------------------------------------------
+# parity of the timed workload (outside every timed region): GPU against the oracle's C port
+# --------------------------------------------------------------------------------------------
+def parity_check(eng, n: int, rank: int, world: int, qbits, om, de, dt, steps: int = 2) -> dict | None:
+    """`steps` mid-ramp sweep steps of the benchmarked workload from a seeded random state, on the GPU (all
+    ranks) and through the C port of the reference path (rank 0, host cores): infidelity and max |delta psi|.
+    qse/calc/qutip.py:34-53; tolerances of BASELINE.json: 1e-10 / 1e-9."""
+    from oracle import c_port
+    from oracle import rydberg_oracle as orc
+
+    p = world.bit_length() - 1
+    nl = n - p
+
+    def shard(r):
+        rng = np.random.default_rng(777 + 64 * n + r)
+        return (rng.standard_normal(1 << nl) + 1j * rng.standard_normal(1 << nl)) / np.sqrt(2.0 ** (n + 1))
+
+    mid = len(om) // 2
+    sel = slice(mid, mid + steps)
+    eng.set_state(shard(rank))
+    eng.evolve_schedule(om[sel], de[sel], dt[sel])
+    got = eng.get_state()
+    if world > 1:
+        from qse_b200 import distributed as qdist
+
+        got = qdist.gather_shards(got)
+    if rank != 0:
+        return None
+    t0 = time.perf_counter()
+    psi = np.concatenate([shard(r) for r in range(world)])
+    c_port.set_threads(os.cpu_count() or 1)
+    e = c_port.build_diagonal(orc.interaction_matrix(qbits.positions), n)
+    want, n_hpsi = c_port.evolve_schedule(psi, e, n, om[sel], de[sel], dt[sel])
+    nrm = float(np.vdot(psi, psi).real)
+    return {"against": "oracle C port (oracle/c/rydberg_ref.c) on the host cores, same seeded state and schedule values",
+            "steps": steps, "infidelity": float(orc.infidelity(got / np.sqrt(nrm), want / np.sqrt(nrm))),
+            "max_abs_dpsi": float(np.max(np.abs(got - want))), "tolerance": {"infidelity": 1e-10, "max_abs_dpsi": 1e-9},
+            "oracle_hpsi": n_hpsi, "seconds": time.perf_counter() - t0}
+
+
+# --------------------------------------------------------------------------------------------
+# north-star configurations (BASELINE.json configs 3, 4, 5): extra keys, outside the headline timing
+# --------------------------------------------------------------------------------------------
+def north_star_single_gpu(local_rank: int, peak: float) -> dict:
+    """Config 3's per-GPU shard size on ONE GPU (kagome 5x2, 30 qubits: 16 GiB of state) and config 5 (28
+    random-position qubits, detuning sweep, bit-string read-out on the device)."""
+    import qse_b200 as qb
+    from qse_b200 import lib
+
+    out = {}
+    a = 0.9 * qb.blockade_radius(OMEGA_MAX)
+    # --- config 3 shard: kagome 30 qubits, quench ------------------------------------------------
+    reg = qb.lattices.kagome(a, 5, 2)
+    n = reg.nqbits
+    t0 = time.perf_counter()
+    with lib.Engine(n, device=local_rank) as eng:
+        eng.set_interaction(qb.interaction_matrix(reg.positions))
+        setup = time.perf_counter() - t0
+        eng.reset_state()
+        T = 2
+        ms = eng.time_schedule(np.full(T, OMEGA_MAX), np.zeros(T), np.full(T, 0.001))  # quench: constant Omega, delta = 0
+        terms = eng.metrics()["last_terms"]
+        norm = eng.norm()
+        hp = np.median(eng.time_apply_h(OMEGA_MAX, 0.0, 5, False)[1:])
+        eng.evolve_schedule(np.full(T, OMEGA_MAX), np.zeros(T), np.full(T, -0.001))
+        idx, pr = eng.topk(1)
+        out["config3_kagome_30q_1gpu"] = {
+            "qubits": n, "hpsi_ms": float(hp), "hpsi_gbs_40B": BYTES_PER_AMP * 2.0 ** n / hp / 1e6,
+            "frac_hbm": BYTES_PER_AMP * 2.0 ** n / hp / 1e6 / peak, "step_ms": [float(x) for x in ms],
+            "steps_per_s": 1e3 / float(np.mean(ms)), "taylor_terms": terms, "norm": norm,
+            "round_trip_infidelity": 1.0 - float(pr[0]) if int(idx[0]) == 0 else 1.0, "setup_s": setup}
+    # --- config 5: 28 random-position qubits, detuning sweep, top-k bit strings --------------------
+    reg = qb.lattices.random_register(28, a, seed=20261019)
+    T = 3
+    amp = qb.Signal(np.full(T, OMEGA_MAX), T)
+    det = qb.Signal(np.linspace(-OMEGA_MAX, 2 * OMEGA_MAX, T), T)
+    calc = qb.B200(reg, amp, det, device=local_rank, return_state=False)
+    t0 = time.perf_counter()
+    calc.calculate()
+    t_calc = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    top = calc.bitstring_probabilities(8)
+    t_top = time.perf_counter() - t0
+    eng = calc._engine
+    hp = np.median(eng.time_apply_h(OMEGA_MAX, 1.0, 5, False)[1:])
+    out["config5_random_28q_mis"] = {
+        "qubits": 28, "calculate_s": t_calc, "steps": T, "topk_s": t_top, "top_bitstring": top[0][0], "top_probability": top[0][1],
+        "norm": eng.norm(), "hpsi_ms": float(hp), "frac_hbm": BYTES_PER_AMP * 2.0 ** 28 / hp / 1e6 / peak,
+        "evolve_s": calc.metrics["evolve_s"], "hpsi_calls": calc.metrics["hpsi_calls"]}
+    calc.close()
+    return out
+
+
+def north_star_8gpu(rank: int, world: int, local_rank: int, peak: float, qdist) -> dict | None:
+    """Config 4: triangular 11x3, 33 qubits, 128 GiB of state over 8 GPUs: H psi x5, two sweep steps, norm,
+    exact time reversal back to |0...0>."""
+    import qse_b200 as qb
+    from qse_b200 import lib
+
+    reg = qb.lattices.triangular(0.9 * qb.blockade_radius(OMEGA_MAX), 11, 3)
+    n = reg.nqbits
+    t0 = time.perf_counter()
+    eng = lib.Engine(n, device=local_rank, rank=rank, nranks=world, nccl_uid=qdist.broadcast_unique_id())
+    eng.set_interaction(qb.interaction_matrix(reg.positions))
+    setup = time.perf_counter() - t0
+    T = 2
+    om = np.linspace(0.3 * OMEGA_MAX, OMEGA_MAX, T)
+    de = np.linspace(-OMEGA_MAX, OMEGA_MAX, T)
+    dt = np.full(T, 0.001)
+    eng.reset_state()
+    ms = eng.time_schedule(om, de, dt)
+    terms = eng.metrics()["last_terms"]
+    norm = eng.norm()
+    hp = qdist.max_over_ranks(float(np.median(eng.time_apply_h(OMEGA_MAX, 0.5, 5, False)[1:])))
+    step = [qdist.max_over_ranks(float(x)) for x in ms]
+    eng.evolve_schedule(om[::-1], de[::-1], -dt[::-1])
+    idx, pr = eng.topk(1)
+    eng.close()
+    if rank != 0:
+        return None
+    amps = 2.0 ** n
+    inbound = 16.0 * amps / world * 2.0 * (world - 1) / world
+    return {"config4_triangular_33q_8gpu": {
+        "qubits": n, "state_gib": amps * 16 / 2 ** 30, "hpsi_ms": hp, "hpsi_gbs_40B_aggregate": BYTES_PER_AMP * amps / hp / 1e6,
+        "frac_hbm": BYTES_PER_AMP * amps / hp / 1e6 / (peak * world), "frac_nvlink": inbound / hp / 1e6 / 770.0,
+        "nvlink_inbound_bytes_per_hpsi_per_gpu": inbound, "step_ms": step, "steps_per_s": 1e3 / float(np.mean(step)),
+        "taylor_terms": terms, "norm": norm, "round_trip_infidelity": 1.0 - float(pr[0]) if int(idx[0]) == 0 else 1.0,
+        "setup_s": setup}}
 
 
 # --------------------------------------------------------------------------------------------
@@ -256,7 +396,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get(str(n if world == 1 else -1))
+            traffic = json.load(fh).get(str(n - p))  # by LOCAL qubits: DRAM bytes of one GPU's own passes
     met = eng.metrics()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
@@ -276,12 +416,15 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                               "(B200_PROFILING.md); nominal 900", "bytes_per_hpsi_per_gpu": inbound,
                               "note": "partner amplitudes are read inside pass 0; time = whole H psi"}
 
+    # ---- parity of this very workload against the oracle (not timed) ---------------------------
+    parity = None if args.no_parity else parity_check(eng, n, rank, world, qbits, om, de, dt)
+
     # ---- e2e: the plugin call with host buffers -------------------------------------------
     eng.close()
     k_amp = qb.Signal(amp.values[W:], K)
     k_det = qb.Signal(det.values[W:], K)
     calc = qb.B200(qbits, qb.Signal(amp.values[:W], W), qb.Signal(det.values[:W], W), device=local_rank,
-                   return_state=(world == 1))
+                   return_state=(True if world == 1 else "shard"))
     calc.calculate()  # warm-up: builds the context and the diagonal
     calc.amplitude, calc.detuning = qb.Signals([k_amp]), qb.Signals([k_det])
     barrier()
@@ -295,7 +438,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     e2e_val = BYTES_PER_AMP * amps_total * e2e_hpsi / t_e2e / 1e9
     state_bytes = out["state"].nbytes if "state" in out else 0
     h2d = (3 * 8 * K) / K
-    d2h = (state_bytes / world + n * 3 * 8) / K
+    d2h = (state_bytes + n * 3 * 8) / K  # per rank: its own shard of the state + the spins
     e2e_launches = calc.metrics["kernel_launches"]
     calc.close()
 
@@ -304,21 +447,28 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         "ms_per_step": 1e3 * t_region / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "complex128", "data": "synthetic",
         "steps_per_s": K / t_region,
-        "config": {"workload": f"square {SHAPES[n][0]}x{SHAPES[n][1]} ({n} qubits) adiabatic sweep, complex128, 1 ns steps",
-                   "amplitudes_per_gpu": 1 << (n - p), "hpsi_per_step": n_hpsi / K,
-                   "l2": "inputs larger than L2 (state 512 MiB/GPU + diagonal 256 MiB vs 126 MB L2); no flush",
-                   "parallelism": f"state sharded by top {p} qubit(s) over {world} GPU(s)", "stepper": "taylor tol 1e-14"},
+        "config": make_config(n, world),
+        "hpsi_per_step": n_hpsi / K,
         "roofline": roofline,
+        "parity": parity,
         "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps_per_s": K / t_e2e, "seconds": t_e2e,
-                "note": "qse_b200.B200.calculate() for the K timed values: schedule upload, sweep, final state "
-                        "copied back to a host ndarray, spins reduced on device"},
+                "note": "qse_b200.B200.calculate() for the K timed values: schedule upload, sweep, spins reduced on "
+                        "the device, final state copied back to a page-locked host ndarray"
+                        + (" (every rank its own shard, return_state='shard'; bytes are per rank)" if world > 1 else "")},
         "gpu_launches": int(launches),
         "e2e_gpu_launches": int(e2e_launches),
         "clocks": clocks,
         "norm_after_sweep": norm,
         "device_event_ms_per_step": float(np.mean(step_ms)),
     }
+    if not args.no_north_star:
+        if world == 1:
+            line["north_star"] = north_star_single_gpu(local_rank, peak)
+        elif world == 8:
+            ns = north_star_8gpu(rank, world, local_rank, peak, qdist)
+            if ns is not None:
+                line["north_star"] = ns
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         gbs, sps, info = cpu_port_run(n, 4, 1, budget_s=40.0)
         line["cpu_baseline"] = {"value": gbs, "unit": "GB/s", "cores": info["cores"], "kind": "port",
@@ -351,6 +501,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--qubits", type=int, default=25, help="qubits per 1-GPU shard (default: BASELINE config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity leg (developer runs)")
+    ap.add_argument("--no-north-star", action="store_true", help="skip the BASELINE config 3/4/5 extras")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rules: W >= 3

@@ -200,8 +200,10 @@ class B200(_Base):
         Termination threshold on the norm of a Taylor term (default 1e-14).
     distributed : bool | None
         Shard over ``torch.distributed`` ranks; ``None`` = when a process group is up.
-    return_state : bool
-        ``False`` keeps the final state on the device (needed from ~28 qubits up).
+    return_state : bool | "shard"
+        ``False`` keeps the final state on the device (needed from ~28 qubits up); ``"shard"`` (sharded
+        runs) returns only this rank's shard, ``(2^(N-p), 1)``, instead of gathering the whole register
+        on every rank.
     wtimes : bool
         Print wall-clock timings like the Pulser / Myqlm calculators do.
     """
@@ -386,7 +388,9 @@ class B200(_Base):
         self._statevector = None
         self.results = None  # drop our own references to the previous state buffer
         result = {}
-        if self.return_state:
+        if self.return_state == "shard":
+            result["state"] = self.local_statevector.reshape(-1, 1)
+        elif self.return_state:
             result["state"] = self.statevector.reshape(-1, 1)
         if e_ops is not None:
             result["expectations"] = exps if exps is not None else np.zeros((omega.size, 0))
@@ -420,6 +424,13 @@ class B200(_Base):
                 local = qdist.gather_shards(local)
             self._statevector = local
         return self._statevector
+
+    @property
+    def local_statevector(self):
+        """This rank's shard of the final state, flat (2^(N-p),) complex128 (the whole state on one GPU)."""
+        if self._engine is None:
+            return None
+        return self._engine.get_state(out=self._state_buffer(self._engine.local_dim))
 
     def _state_buffer(self, n: int):
         """Page-locked host buffer for the state read-back (PCIe speed instead of a staged copy).

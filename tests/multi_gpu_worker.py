@@ -120,12 +120,13 @@ def main():
             failures.append(name)
 
     omega_max = 2 * np.pi
-    for exchange in ("ipc", "nccl"):
+    quick = os.environ.get("QSB_WORKER_QUICK", "0") != "0"  # __graft_entry__.smoke(): one size, peer-memory exchange
+    for exchange in (("ipc",) if quick else ("ipc", "nccl")):
         if exchange == "nccl":
             os.environ["QSB_NO_IPC"] = "1"
         else:
             os.environ.pop("QSB_NO_IPC", None)
-        for n in ((8, 14, 17, 19) if world >= 4 else (8, 14, 17)):
+        for n in ((14,) if quick else (8, 14, 17, 19) if world >= 4 else (8, 14, 17)):
             reg = qb.lattices.random_register(n, 0.9 * qb.blockade_radius(omega_max), seed=n)
             plan = qdist.ShardPlan(n, world)
             v = orc.interaction_matrix(reg.positions)
@@ -195,7 +196,7 @@ def main():
             check(f"{exchange} n={n} sweep spins", d <= 1e-9, f"{d:.2e}")
             calc.close()
     os.environ.pop("QSB_NO_IPC", None)
-    if os.environ.get("QSB_WORKER_LARGE", "1") != "0":
+    if os.environ.get("QSB_WORKER_LARGE", "1") != "0" and not quick:
         large_shard_cases(rank, world, local, check)
     t = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(t)
