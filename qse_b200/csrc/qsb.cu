@@ -676,6 +676,9 @@ static int evolve_segment_impl(qsb_ctx* c, const HParams& hp, double dt, int* n_
         return QSB_OK;
     }
     nvtx_push("qsb:segment");
+    // term 1 reads the partners' psi over NVLink: whatever wrote psi before this segment (qsb_set_state, a
+    // checkpoint load, the axpy of a one-term step) must be complete on EVERY rank, not just on this one
+    TRY(rank_barrier(c));
     for (int sub = 0; sub < nsub; ++sub) {
         c->met.substeps++;
         // Term 1 reads psi directly.  Terms are accumulated into psi in PAIRS -- the even term adds its
@@ -692,7 +695,10 @@ static int evolve_segment_impl(qsb_ctx* c, const HParams& hp, double dt, int* n_
             TRY(taylor_term(c, hp, h, j, acc_mode, &x));
             ++applied;
         }
-        if (planned == 1) TRY(axpy_vec(c, c->psi, x));  // x_0 IS psi: term 1 could not update it in place
+        if (planned == 1) {  // x_0 IS psi: term 1 could not update it in place
+            TRY(axpy_vec(c, c->psi, x));
+            TRY(rank_barrier(c));  // a partner's next term must not read psi before this update
+        }
         int m = planned;
         if (c->fixed_terms == 0) {
             TRY(fetch_slots(c, 1, (size_t)planned));  // ONE synchronisation per sub-step
