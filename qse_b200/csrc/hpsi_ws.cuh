@@ -87,7 +87,19 @@ struct WsItem {
     double dhi;    // FIRST: diagonal of the tile base (index bits >= TB and the rank's bits): pairs + single-bit terms
     double w[12];  // FIRST, diagonal on the fly: w[b] = sum over the set high bits h of the base of V(h, b), tile bit b
     int type;
-    int sb;
+    int sb;        // super-block of the tile; kItemPeer: which sharded qubit's coefficient applies
+    int n_follow;  // sharded state: partner stages (kItemPeer) that follow this tile in the ring
+};
+
+// ring state a consumer carries into ws_process when partner stages follow the tile it is working on
+struct WsRing {
+    double2* tiles;
+    uint64_t* full_bar;
+    uint64_t* empty_bar;
+    const WsItem* desc;
+};
+struct PeerMaps {
+    CUtensorMap m[8];  // strided (plain-launch) tiles of the partners' x (direct exchange) or Z chunks (remap)
 };
 
 struct HpsiWs {
@@ -97,7 +109,13 @@ struct HpsiWs {
     double2* acc;
     double* norm_part;
     const double2* peer[kMaxPeers];
-    int n_peer;
+    int n_peer;      // partner stages per tile that takes part in the exchange in THIS launch (0: none)
+    // Which tiles pull their partners in this launch (the NVLink traffic of one H psi is spread over the fused
+    // and the last plain launch): 0 = every tile, 1 = tiles with index bit peer_bit CLEAR, 2 = tiles with it SET.
+    // peer_bit lies inside the super-block index above the contiguous tile, so it is constant over a contiguous
+    // tile and over a strided tile of the plain launch alike.
+    int peer_sel;
+    int peer_bit;
     SiteParams sp;   // per-site Omega_q / 2 and delta_q by index bit (hw_peer = 1.0 with the remap exchange)
     // Diagonal on the fly (otf = 1): the diagonal of H is 2-local,
     //     d(k) = c0 + sum_b lin[b] b_b(k) + sum_{b<b'} vbits[b][b'] b_b(k) b_b'(k)       (LOCAL index bits b),
@@ -134,6 +152,7 @@ struct HpsiWs {
     int remap;
     int rank;
     int cbits;       // log2 of the chunk (= shard / P)
+    int pbits;       // log2 P
     unsigned int sb_xor;  // remap: super-block order staggered per rank (rank r starts in chunk r) so that at any
                      // moment the ranks pull from DIFFERENT sources instead of all hammering one GPU's links
     const double2* zpeer[8];
@@ -154,7 +173,7 @@ struct RemapArgs {
     int cbits;
 };
 template <int P>
-__global__ void __launch_bounds__(256) remap_z_kernel(const RemapArgs a) {
+__global__ void __launch_bounds__(1024, 1) remap_z_kernel(const RemapArgs a) {
     const u64 clen = 1ull << a.cbits;
     const u64 src0 = (u64)a.rank << a.cbits;
     for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < clen; w += (u64)gridDim.x * blockDim.x) {
@@ -223,12 +242,15 @@ QSB_DEV void cfma(double2& v, double c, double2 x) {
 // address.  Global operands (the partial y; E when the diagonal is not computed on the fly) are
 // requested up front with loads the compiler may not sink and are CONSUMED LAST, after the
 // shared-memory flip phase, so that their L2 / HBM latency hides behind it.
-// PEER (FIRST only, sharded state): the producer has already pulled the partner tiles over NVLink
-// (kItemPeer stages, ws_peer below) and y holds sum_g hw_g * partner_g.
+// Sharded state: n_follow partner stages (kItemPeer) follow the tile in the ring -- the same 2^TB amplitudes
+// of a partner GPU's x (or of a remap buffer), pulled over NVLink by the producer's TMA copies.  They are folded
+// into the accumulators after the flip phase, straight from shared memory: the transfer latency sits in the
+// ring like any other tile load, no consumer ever stalls on an NVLink access and nothing takes a detour
+// through y.
 // diag: FIRST only -- the diagonal of H for this thread's 8 amplitudes.
-template <int TB, bool FIRST, bool PEER, bool LAST>
+template <int TB, bool FIRST, bool LAST>
 QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 base, int t, const double (&diag)[kPerThread],
-                        double& red, uint64_t* empty) {
+                        double& red, uint64_t* empty, const WsRing& ring, int n_follow, u64& it) {
     using C = WsCfg<TB>;
     const int lb = FIRST ? TB : p.lb;
     const int hb0 = FIRST ? TB : p.hb0;
@@ -244,11 +266,11 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
     (FIRST ? (u64)((j)*C::kGroupThreads) : (((((u64)((j)*C::kGroupThreads)) >> lb) << hb0) | (((u64)((j)*C::kGroupThreads)) & low_mask)))
 #define QSB_GADDR(j) (g0 + QSB_GOFF(j))
 
-    constexpr bool kHaveY = !FIRST || PEER;
+    constexpr bool kHaveY = !FIRST;
     double2 yv[kHaveY ? kPerThread : 1];
     double2 v[kPerThread];
     // the partial y (non-FIRST; L2-resident: written by the FIRST tiles of this super-block, or prefetched
-    // by the producer) or the partners' term (FIRST + PEER)
+    // by the producer)
     if constexpr (kHaveY) {
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) yv[j] = ldcg2(p.y + QSB_GADDR(j));
@@ -294,6 +316,18 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
     if constexpr (kHaveY) {
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) cacc(v[j], yv[j]);
+    }
+    // partner stages: v += hw_g * partner tile (same tile geometry, so the same shared-memory index)
+    for (int f = 0; f < n_follow; ++f) {
+        it += C::kGroups;
+        const int s2 = (int)(it % C::kStages);
+        mbar_wait(&ring.full_bar[s2], (uint32_t)((it / C::kStages) & 1ull));
+        const double h = p.sp.hw_peer[ring.desc[s2].sb];
+        const double2* zs = ring.tiles + (size_t)s2 * C::kTileW;
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) cfma(v[j], h, zs[QSB_IDX(j)]);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&ring.empty_bar[s2]);
     }
     // output addresses are formed only now (same trick): no 64-bit address lives through the flip phase
     const u64 ge = g0 + ((u64)__double_as_longlong(v[0].x) & p.zero);
@@ -342,29 +376,11 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
 #undef QSB_IDX
 }
 
-// A partner GPU's tile (the sharded-qubit flip of the same 2^TB amplitudes), pulled over NVLink by
-// the producer's TMA copies into an ordinary stage: y = hw_g * partner  (first partner) or
-// y += hw_g * partner.  The FIRST item of the same tile follows in the same CTA, so the same
-// thread re-reads what it wrote: program order is the only synchronisation needed, and no consumer
-// ever stalls on an NVLink load -- the transfer latency sits in the stage ring like any other tile.
-template <int TB>
-QSB_DEV void ws_peer(const HpsiWs& p, const double2* __restrict__ ts, u64 base, int q, int t) {
-    using C = WsCfg<TB>;
-    const double h = p.sp.hw_peer[q];
-#pragma unroll
-    for (int j = 0; j < kPerThread; ++j) {
-        const int idx = t + j * C::kGroupThreads;
-        const double2 v = ts[idx];
-        double2 out = make_double2(h * v.x, h * v.y);
-        if (q > 0) cacc(out, ldcg2(p.y + base + idx));
-        p.y[base + idx] = out;
-    }
-}
-
 template <int TB>
 __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, const __grid_constant__ CUtensorMap tmap,
                                                                 const __grid_constant__ CUtensorMap tmap_y,
-                                                                const __grid_constant__ CUtensorMap tmap_acc) {
+                                                                const __grid_constant__ CUtensorMap tmap_acc,
+                                                                const __grid_constant__ PeerMaps pmaps) {
     using C = WsCfg<TB>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2* tiles = reinterpret_cast<double2*>(smem_raw);
@@ -419,8 +435,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
             const u64 lag = p.fused ? ((u64)p.lag < n_sb ? (u64)(p.lag < 1 ? 1 : p.lag) : n_sb) : 0;
             const u64 total = p.fused ? 2ull * p.n_tiles : p.n_tiles;
             int n_done = 0;
-            int peer_left = 0;         // partner stages still to publish for the pending FIRST tile
-            bool first_pending = false;
+            int peer_left = 0;         // partner stages still to publish behind the tile just issued
+            bool pend_first = false;   // ... which was a contiguous (FIRST) tile / a strided one
             u64 pend_tau = 0;
             // Tickets are claimed in batches of p.tk_batch with ONE atomic, and the claim of the NEXT batch is
             // issued when a batch starts: its round trip (~1 us with every SM on the same counter) hides behind
@@ -438,8 +454,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                 const u64 use = it / C::kStages;
                 int type = kItemDone;
                 u64 tau = 0;
-                if (peer_left > 0 || first_pending) {
-                    type = peer_left > 0 ? kItemPeer : kItemFirst;
+                if (peer_left > 0) {
+                    type = kItemPeer;
                     tau = pend_tau;
                 } else {
                     if (n_done == 0 && left == 0) {
@@ -461,13 +477,6 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                             type = ws_decode_ticket(ticket, n_a, n_sb, lag, (u64)p.sb_xor, &tau);
                         }
                     }
-                    if (type == kItemFirst && p.n_peer > 0) {
-                        // sharded state: the partner tiles go first, one stage each, then the tile itself
-                        pend_tau = tau;
-                        peer_left = p.n_peer;
-                        first_pending = true;
-                        type = kItemPeer;
-                    }
                 }
                 // diagonal of a contiguous tile's base (identical for its 2^TB amplitudes), computed while the
                 // stage is still busy: lane b < TB sums V(h, b) over the set high bits h (the single-bit offset of
@@ -486,23 +495,46 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                 }
                 if (use > 0) mbar_wait(&empty_bar[s], (uint32_t)((use - 1) & 1ull));
                 if (type == kItemPeer) {
+                    // partner stage: the SAME amplitudes as the tile just issued, from a partner GPU's x (direct
+                    // exchange: one stage per sharded qubit) or from the remap buffers (one stage), pulled over
+                    // NVLink by the TMA engine into an ordinary stage of the ring
                     const int q = p.n_peer - peer_left;
                     --peer_left;
-                    const u64 pbase = tau << TB;
                     double2* pstage = tiles + (size_t)s * C::kTileW;
                     if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(C::kTileW * sizeof(double2)));
                     __syncwarp();
-                    constexpr int kCopies = 4;
-                    constexpr int chunk = C::kTileW / kCopies;
-                    const double2* psrc = p.peer[q] + pbase;
-                    if (p.remap) {
-                        const int tcb = p.cbits - TB;  // tiles per chunk (log2)
-                        psrc = p.zpeer[tau >> tcb] + ((u64)p.rank << p.cbits) + ((tau & ((1ull << tcb) - 1ull)) << TB);
+                    if (pend_first) {
+                        const u64 pbase = tau << TB;
+                        constexpr int kCopies = 4;
+                        constexpr int chunk = C::kTileW / kCopies;
+                        const double2* psrc = p.peer[q] + pbase;
+                        if (p.remap) {
+                            const int tcb = p.cbits - TB;  // tiles per chunk (log2)
+                            psrc = p.zpeer[tau >> tcb] + ((u64)p.rank << p.cbits) + ((tau & ((1ull << tcb) - 1ull)) << TB);
+                        }
+                        if (lane < kCopies)
+                            bulk_g2s(pstage + lane * chunk, psrc + (u64)lane * chunk, chunk * sizeof(double2), &full_bar[s]);
+                    } else {
+                        const int mid_bits = p.hb0 - p.lb;
+                        const int c0 = (int)((tau & ((1ull << mid_bits) - 1ull)) << (p.lb + 1));
+                        const int c1 = (int)((tau >> mid_bits) << p.hb);
+                        const int rows = 1 << p.hb;
+                        if (p.remap) {
+                            // the rows of a strided tile fall into P groups by their top index bits = the rank whose
+                            // remap buffer holds them: one box of 2^(hb - pbits) rows per source
+                            const int rpc = p.hb - p.pbits;
+                            if (lane < (1 << p.pbits)) tma_load_2d(pstage + ((size_t)(lane << rpc) << p.lb), &pmaps.m[lane], c0, 0, &full_bar[s]);
+                        } else if (p.use_tmap) {
+                            const int n_box = (rows + 255) >> 8;
+                            if (lane < n_box) tma_load_2d(pstage + ((size_t)(lane * 256) << p.lb), &pmaps.m[q], c0, c1 + lane * 256, &full_bar[s]);
+                        } else {
+                            const u64 pbase = ws_tile_base(p.lb, p.hb, p.hb0, tau);
+                            const uint32_t row_bytes = (uint32_t)(sizeof(double2) << p.lb);
+                            for (int r = lane; r < rows; r += 32)
+                                bulk_g2s(pstage + ((size_t)r << p.lb), p.peer[q] + pbase + ((u64)r << p.hb0), row_bytes, &full_bar[s]);
+                        }
                     }
-                    if (lane < kCopies)  // TMA pull from the partner's HBM over NVLink
-                        bulk_g2s(pstage + lane * chunk, psrc + (u64)lane * chunk, chunk * sizeof(double2), &full_bar[s]);
                     if (lane == 0) {
-                        desc[s].base = pbase;
                         desc[s].type = kItemPeer;
                         desc[s].sb = q;
                         mbar_arrive(&full_bar[s]);
@@ -510,7 +542,6 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                     __syncwarp();
                     continue;
                 }
-                first_pending = false;
                 if (type == kItemDone) {
                     // out of work: one sentinel per consumer group (consecutive items go to distinct groups)
                     if (lane == 0) {
@@ -557,6 +588,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                             bulk_g2s(stage + ((size_t)r << p.lb), p.x + base + ((u64)r << p.hb0), row_bytes, &full_bar[s]);
                     }
                 }
+                // does this tile pull its partners in THIS launch?
+                const int n_follow = (p.n_peer > 0 && type != kItemInner &&
+                                      (p.peer_sel == 0 || (int)((base >> p.peer_bit) & 1ull) == (p.peer_sel == 2 ? 1 : 0)))
+                                         ? p.n_peer : 0;
                 if (type == kItemFirst) {
                     if (lane < TB) desc[s].w[lane] = wl;
                     if (lane == 0) desc[s].dhi = eh + p.c0;
@@ -570,7 +605,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                     desc[s].base = base;
                     desc[s].type = type;
                     desc[s].sb = sb;
+                    desc[s].n_follow = n_follow;
                     mbar_arrive(&full_bar[s]);  // release: descriptor (and the INNER dependency) visible to consumers
+                }
+                if (n_follow > 0) {
+                    peer_left = n_follow;
+                    pend_tau = tau;
+                    pend_first = (type == kItemFirst);
                 }
                 __syncwarp();
             }
@@ -612,6 +653,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
             }
         }
         unsigned int n_first = 0;  // contiguous tiles this CTA has processed (publisher sequence number)
+        const WsRing ring{tiles, full_bar, empty_bar, desc};
         for (u64 it = (u64)group;; it += C::kGroups) {
             const int s = (int)(it % C::kStages);
             const u64 use = it / C::kStages;
@@ -630,6 +672,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
             }
             const u64 base = desc[s].base;
             const int sb = desc[s].sb;
+            const int n_follow = desc[s].n_follow;
             const double2* ts = tiles + (size_t)s * C::kTileW;
             if (type == kItemFirst) {
                 // + the tile-base part: its own terms (dhi) and its coupling to this thread's tile bits (w);
@@ -655,8 +698,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
 #pragma unroll
                     for (int j = 0; j < kPerThread; ++j) diag[j] += ldnc1(p.eint + base + tg + j * C::kGroupThreads);
                 }
-                if (p.n_peer > 0) ws_process<TB, true, true, false>(p, ts, base, tg, diag, part, &empty_bar[s]);
-                else ws_process<TB, true, false, false>(p, ts, base, tg, diag, part, &empty_bar[s]);
+                ws_process<TB, true, false>(p, ts, base, tg, diag, part, &empty_bar[s], ring, n_follow, it);
                 // publish this tile of partial y: warp barrier -> cta-scope release on the shared
                 // counter; the last warp of the group to finish issues ONE gpu-scope fence (cumulative
                 // over the writes it observed through the counter) and bumps the super-block counter.
@@ -683,14 +725,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                         atomicAdd(p.done + sb, 1ull);
                     }
                 }
-            } else if (type == kItemPeer) {
-                ws_peer<TB>(p, ts, base, sb, tg);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[s]);
             } else {
                 const double nodiag[kPerThread] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                if (p.last) ws_process<TB, false, false, true>(p, ts, base, tg, nodiag, part, &empty_bar[s]);
-                else ws_process<TB, false, false, false>(p, ts, base, tg, nodiag, part, &empty_bar[s]);
+                if (p.last) ws_process<TB, false, true>(p, ts, base, tg, nodiag, part, &empty_bar[s], ring, n_follow, it);
+                else ws_process<TB, false, false>(p, ts, base, tg, nodiag, part, &empty_bar[s], ring, n_follow, it);
             }
         }
     }

@@ -69,7 +69,7 @@ struct qsb_ctx {
     int use_tmap = 1;  // option "tensor_map": 2-D tensor-map TMA for strided tiles (0 = one bulk copy per row)
     struct TmapEntry {
         const void* ptr;
-        int lb, hb, hb0;
+        int lb, hb, hb0, rows_log2, box_rows_log2;
         CUtensorMap map;
     };
     std::vector<TmapEntry> tmaps;  // super-block size the completion counters were accumulated with
@@ -108,6 +108,11 @@ struct qsb_ctx {
     double2* zbuf = nullptr;                // remap exchange: neighbour sums in the transposed layout
     double2* peer_z[64] = {nullptr};
     int exchange = -1;                      // option "exchange": -1 auto, 0 direct partner pulls, 1 remap
+    int exchange_split = -1;                // option "exchange_split": where the partner tiles are pulled: -1 auto, 0 fused
+                                            // launch, 1 half in the fused and half in the last plain launch, 2 plain launch
+    int remap_ctas = 24;                    // option "remap_ctas": SMs the remap kernel takes beside the fused launch
+    cudaStream_t stream2 = nullptr;         // the remap kernel runs beside the fused launch (sharded contexts)
+    cudaEvent_t ev_x = nullptr, ev_z = nullptr;
     // measurement
     double* flush_buf = nullptr;
     size_t flush_n = 0;
@@ -262,9 +267,13 @@ static WsPlan make_ws_plan(int nl, int sb_bits, int tile_bits) {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int get_tmap(qsb_ctx* c, const double2* x, int lb, int hb, int hb0, const CUtensorMap** out) {
+// rows_log2 / box_rows_log2 < 0: the whole shard ({2^(nl - hb0) rows}, boxes of min(2^hb, 256) rows)
+static int get_tmap(qsb_ctx* c, const double2* x, int lb, int hb, int hb0, const CUtensorMap** out, int rows_log2 = -1,
+                    int box_rows_log2 = -1) {
+    if (rows_log2 < 0) rows_log2 = c->nl - hb0;
+    if (box_rows_log2 < 0) box_rows_log2 = std::min(hb, 8);
     for (auto& e : c->tmaps)
-        if (e.ptr == x && e.lb == lb && e.hb == hb && e.hb0 == hb0) {
+        if (e.ptr == x && e.lb == lb && e.hb == hb && e.hb0 == hb0 && e.rows_log2 == rows_log2 && e.box_rows_log2 == box_rows_log2) {
             *out = &e.map;
             return QSB_OK;
         }
@@ -281,9 +290,11 @@ static int get_tmap(qsb_ctx* c, const double2* x, int lb, int hb, int hb0, const
     e.lb = lb;
     e.hb = hb;
     e.hb0 = hb0;
-    const cuuint64_t gdim[2] = {2ull << hb0, 1ull << (c->nl - hb0)};
+    e.rows_log2 = rows_log2;
+    e.box_rows_log2 = box_rows_log2;
+    const cuuint64_t gdim[2] = {2ull << hb0, 1ull << rows_log2};
     const cuuint64_t gstride[1] = {16ull << hb0};
-    const cuuint32_t box[2] = {2u << lb, (cuuint32_t)std::min(1 << hb, 256)};
+    const cuuint32_t box[2] = {2u << lb, 1u << box_rows_log2};
     const cuuint32_t estride[2] = {1, 1};
     const CUresult r = encode(&e.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)x, gdim, gstride, box, estride,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -408,6 +419,22 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, const HParam
     a.c0 = hp.c0;
     // remap exchange: from 4 ranks up, when peer memory is mapped and a chunk holds whole tiles
     const bool remap = c->nranks >= 4 && c->nranks <= 8 && c->ipc && c->zbuf && c->exchange != 0 && (c->nl - c->p) >= w.tb;
+    const int np = c->p == 0 ? 0 : (remap ? 1 : c->p);  // partner stages per tile
+    // Where the partner tiles are pulled (hpsi_ws.cuh, peer_sel): the NVLink traffic should run beside ALL the local
+    // work of an H psi, not beside one launch only.
+    //   direct exchange: half of the tiles pull in the fused launch, the other half in the last plain launch;
+    //   remap exchange : the remap kernel runs BESIDE the fused launch (own stream, its own SMs), every tile
+    //                    pulls its Z rows in the last plain launch.
+    const PassGeom gl = w.n_plain > 0 ? w.plain[w.n_plain - 1] : w.inner;
+    const bool plain_ok = w.n_plain > 0 && np > 0 && (!remap || (gl.hb >= c->p && gl.hb0 + gl.hb == c->nl && c->use_tmap && gl.lb <= 7));
+    int split = c->exchange_split;
+    if (split < 0) split = plain_ok ? (remap ? 2 : 1) : 0;
+    if (!plain_ok) split = 0;
+    // the plain launch that ends a Taylor term keeps its own tile while the partner stages pass through the ring:
+    // with 3 stages that leaves room for two of them
+    if (!remap && split != 0 && np > 2) split = 0;
+    const bool concurrent_remap = remap && split == 2 && c->stream2 && c->remap_ctas > 0 && c->remap_ctas < c->n_sm;
+    const int grid_fused = concurrent_remap ? std::max(1, std::min(grid, c->n_sm - c->remap_ctas)) : grid;
     if (remap) {
         RemapArgs ra{};
         for (int r = 0; r < c->nranks; ++r) {
@@ -419,25 +446,39 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, const HParam
         ra.z = c->zbuf;
         ra.rank = c->rank;
         ra.cbits = c->nl - c->p;
-        const int rgrid = grid_for(c, 1ull << ra.cbits, 256);
         nvtx_push("qsb:remap_exchange");
-        if (c->nranks == 4) remap_z_kernel<4><<<rgrid, 256, 0, c->stream>>>(ra);
-        else remap_z_kernel<8><<<rgrid, 256, 0, c->stream>>>(ra);
-        LAUNCHED(c);
-        TRY(check_launch(c, "remap_z_kernel"));
-        TRY(rank_barrier(c));  // every rank's Z must be complete before anyone pulls from it
+        if (concurrent_remap) {
+            // x is final once everything queued on the main stream so far has run; the remap kernel then owns
+            // remap_ctas SMs (one 1024-thread CTA each) while the fused launch runs on the others
+            CU(cudaEventRecord(c->ev_x, c->stream));
+            CU(cudaStreamWaitEvent(c->stream2, c->ev_x, 0));
+            if (c->nranks == 4) remap_z_kernel<4><<<c->remap_ctas, 1024, 0, c->stream2>>>(ra);
+            else remap_z_kernel<8><<<c->remap_ctas, 1024, 0, c->stream2>>>(ra);
+            LAUNCHED(c);
+            TRY(check_launch(c, "remap_z_kernel"));
+            CU(cudaEventRecord(c->ev_z, c->stream2));
+        } else {
+            const int rgrid = std::max(1, grid_for(c, 1ull << ra.cbits, 1024) / 4);
+            if (c->nranks == 4) remap_z_kernel<4><<<rgrid, 1024, 0, c->stream>>>(ra);
+            else remap_z_kernel<8><<<rgrid, 1024, 0, c->stream>>>(ra);
+            LAUNCHED(c);
+            TRY(check_launch(c, "remap_z_kernel"));
+            TRY(rank_barrier(c));  // every rank's Z must be complete before anyone pulls from it
+        }
         nvtx_pop();
         a.remap = 1;
         a.rank = c->rank;
         a.cbits = ra.cbits;
-        a.sb_xor = (ra.cbits >= w.sbits) ? ((unsigned int)c->rank << (ra.cbits - w.sbits)) : 0u;
+        a.pbits = c->p;
+        // contiguous tiles pull from ONE source each: stagger the super-block order per rank (no NVLink hot spot)
+        a.sb_xor = (split != 2 && ra.cbits >= w.sbits) ? ((unsigned int)c->rank << (ra.cbits - w.sbits)) : 0u;
         for (int g = 0; g < kMaxPeers; ++g) a.sp.hw_peer[g] = 1.0;  // the coefficients are already in Z
     }
     a.x = x;
     a.y = y;
     a.eint = c->eint;
     for (int g = 0; g < kMaxPeers; ++g) a.peer[g] = peers[g];
-    a.n_peer = remap ? 1 : c->p;
+    a.peer_bit = w.sbits - 1;
     a.scale = fuse ? scale : make_double2(1.0, 0.0);
     a.nl = c->nl;
     a.done = c->sb_done;
@@ -452,6 +493,23 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, const HParam
         a.hb0 = g.hb0;
         a.last = (last && fuse) ? 1 : 0;
         a.lag = c->sb_lag > 0 ? c->sb_lag : auto_sb_lag(w.sbits);
+        // partner stages of this launch
+        if (i == 0) {
+            a.n_peer = (split == 2) ? 0 : np;
+            a.peer_sel = (split == 1) ? 1 : 0;
+        } else if (last) {
+            a.n_peer = (split == 0) ? 0 : np;
+            a.peer_sel = (split == 1) ? 2 : 0;
+        } else {
+            a.n_peer = 0;
+            a.peer_sel = 0;
+        }
+        const int lgrid = (i == 0) ? grid_fused : grid;
+        if (i == 1 && concurrent_remap) {
+            // the fused launch is queued; Z must be complete on EVERY rank before the plain launch pulls from it
+            CU(cudaStreamWaitEvent(c->stream, c->ev_z, 0));
+            TRY(rank_barrier(c));
+        }
 
         a.acc_mode = (fuse && last) ? acc_mode : kAccNone;
         a.red_mode = red_mode;
@@ -463,8 +521,8 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, const HParam
         a.ticket = c->tickets + i;
         {
             const u64 total = a.fused ? 2 * n_tiles : n_tiles;
-            a.tk_batch = c->tk_batch > 0 ? c->tk_batch : auto_ticket_batch(total, grid);
-            a.ticket_base = take_tickets(c, i, total, grid, a.tk_batch);
+            a.tk_batch = c->tk_batch > 0 ? c->tk_batch : auto_ticket_batch(total, lgrid);
+            a.ticket_base = take_tickets(c, i, total, lgrid, a.tk_batch);
         }
         if (i == 0) {
             if (c->ws_sbits_active != w.sbits * 16 + w.tb) {
@@ -492,8 +550,27 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, const HParam
             tm_y = &tm_y_copy;
             if (a.acc) TRY(get_tmap(c, a.acc, g.lb, g.hb, g.hb0, &tm_acc));
         }
-        if (w.tb == 11) hpsi_ws_kernel<11><<<grid, kWsThreads, kWsSmemBytes, c->stream>>>(a, *tm, *tm_y, *tm_acc);
-        else hpsi_ws_kernel<12><<<grid, kWsThreads, kWsSmemBytes, c->stream>>>(a, *tm, *tm_y, *tm_acc);
+        // strided partner tiles: the same boxes out of the partners' x (direct), or one box of rows per source rank
+        // out of chunk `rank` of its remap buffer
+        PeerMaps pm;
+        memset(&pm, 0, sizeof(pm));
+        if (i > 0 && a.n_peer > 0 && a.use_tmap) {
+            const CUtensorMap* t = nullptr;
+            if (remap) {
+                const int rpc = g.hb - c->p;
+                for (int r = 0; r < c->nranks; ++r) {
+                    TRY(get_tmap(c, c->peer_z[r] + ((u64)c->rank << a.cbits), g.lb, g.hb, g.hb0, &t, rpc, rpc));
+                    pm.m[r] = *t;
+                }
+            } else {
+                for (int q = 0; q < c->p; ++q) {
+                    TRY(get_tmap(c, peers[q], g.lb, g.hb, g.hb0, &t));
+                    pm.m[q] = *t;
+                }
+            }
+        }
+        if (w.tb == 11) hpsi_ws_kernel<11><<<lgrid, kWsThreads, kWsSmemBytes, c->stream>>>(a, *tm, *tm_y, *tm_acc, pm);
+        else hpsi_ws_kernel<12><<<lgrid, kWsThreads, kWsSmemBytes, c->stream>>>(a, *tm, *tm_y, *tm_acc, pm);
         LAUNCHED(c);
         TRY(check_launch(c, "hpsi_ws_kernel"));
     }
@@ -1031,6 +1108,13 @@ static int setup_comm(qsb_ctx* c, const void* uid_bytes) {
     TRY(allreduce(c, c->slots, 1, kNcclSum));
     TRY(fetch_slots(c, 0, 1));
     c->ipc = (c->h_slots[0] == 0.0);
+    if (c->ipc && c->zbuf) {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, hi));
+        CU(cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_z, cudaEventDisableTiming));
+    }
     if (!c->ipc) {
         for (int g = 0; g < c->p; ++g) CU(cudaMalloc(&c->stage[g], c->dim * sizeof(double2)));
     }
@@ -1196,6 +1280,12 @@ int qsb_destroy(qsb_ctx* c) {
     cudaFree(c->sched_dev);
     cudaFree(c->sb_done);
     if (c->h_slots) cudaFreeHost(c->h_slots);
+    if (c->stream2) {
+        cudaStreamSynchronize(c->stream2);
+        cudaStreamDestroy(c->stream2);
+    }
+    if (c->ev_x) cudaEventDestroy(c->ev_x);
+    if (c->ev_z) cudaEventDestroy(c->ev_z);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1247,6 +1337,12 @@ int qsb_set_option(qsb_ctx* c, const char* key, double value) {
     } else if (!strcmp(key, "exchange")) {
         if (value != -1.0 && value != 0.0 && value != 1.0) return fail(c, QSB_ERR_INVALID, "exchange must be -1, 0 or 1");
         c->exchange = (int)value;
+    } else if (!strcmp(key, "exchange_split")) {
+        if (value != -1.0 && value != 0.0 && value != 1.0 && value != 2.0) return fail(c, QSB_ERR_INVALID, "exchange_split must be -1, 0, 1 or 2");
+        c->exchange_split = (int)value;
+    } else if (!strcmp(key, "remap_ctas")) {
+        if (value < 0 || value > 128) return fail(c, QSB_ERR_INVALID, "remap_ctas must be in 0..128");
+        c->remap_ctas = (int)value;
     } else if (!strcmp(key, "ticket_batch")) {
         if (value < 0 || value > 64) return fail(c, QSB_ERR_INVALID, "ticket_batch must be 0 (auto) or in 1..64");
         c->tk_batch = (int)value;

@@ -49,10 +49,19 @@ def large_shard_cases(rank, world, local, check):
     eng.set_interaction(qb.interaction_matrix(qbits.positions))
     eng.set_state(mine)
     y = {"default": eng.apply_h(om[11], de[11])}
+    # every placement of the partner pulls: fused launch only / split between the launches / plain launch only,
+    # with the direct and (from 4 ranks) the remap exchange, the remap kernel beside the fused launch or before it
+    variants = [("direct, fused", {"exchange": 0, "exchange_split": 0}), ("direct, split", {"exchange": 0, "exchange_split": 1}),
+                ("direct, plain", {"exchange": 0, "exchange_split": 2})]
     if world >= 4:
-        eng.set_option("exchange", 0)
-        y["direct"] = eng.apply_h(om[11], de[11])
-        eng.set_option("exchange", -1)
+        variants += [("remap, fused", {"exchange": 1, "exchange_split": 0}), ("remap, plain", {"exchange": 1, "exchange_split": 2}),
+                     ("remap, plain, serial", {"exchange": 1, "exchange_split": 2, "remap_ctas": 0})]
+    for name, opts in variants:
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        y[name] = eng.apply_h(om[11], de[11])
+        for k, v in {"exchange": -1, "exchange_split": -1, "remap_ctas": 24}.items():
+            eng.set_option(k, v)
     eng.evolve_schedule(om[sel], de[sel], dt[sel])
     evolved = eng.get_state()
     spins = eng.spins()
@@ -69,7 +78,7 @@ def large_shard_cases(rank, world, local, check):
         want_h = c_port.apply_h(psi, e, n, om[11], de[11])
         for k, got in full_y.items():
             err = float(np.max(np.abs(got - want_h)) / np.max(np.abs(want_h)))
-            check(f"large n={n} H psi ({k} exchange) vs C port", err <= 1e-13, f"rel err {err:.2e}")
+            check(f"large n={n} H psi ({k}) vs C port", err <= 1e-13, f"rel err {err:.2e}")
         want, _ = c_port.evolve_schedule(psi, e, n, om[sel], de[sel], dt[sel])
         nrm = float(np.vdot(psi, psi).real)
         infid = orc.infidelity(full_e / np.sqrt(nrm), want / np.sqrt(nrm))
