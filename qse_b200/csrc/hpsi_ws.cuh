@@ -174,22 +174,35 @@ struct RemapArgs {
 };
 template <int P>
 __global__ void __launch_bounds__(1024, 1) remap_z_kernel(const RemapArgs a) {
+    // U amplitudes per thread and trip: 8 peer loads of 16 bytes in flight per thread (128 KiB per SM), which is
+    // what it takes to keep an NVLink at ~3 us of latency busy from the few SMs this kernel is given
+    constexpr int U = 8 / P;
     const u64 clen = 1ull << a.cbits;
     const u64 src0 = (u64)a.rank << a.cbits;
-    for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < clen; w += (u64)gridDim.x * blockDim.x) {
-        double2 v[P];
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 w0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; w0 < clen; w0 += stride * U) {
+        double2 v[U][P];
 #pragma unroll
-        for (int c = 0; c < P; ++c) v[c] = ldg2_volatile(a.xs[c] + src0 + w);
+        for (int u = 0; u < U; ++u) {
+            const u64 w = w0 + (u64)u * stride;
 #pragma unroll
-        for (int c = 0; c < P; ++c) {
-            double2 s = make_double2(0.0, 0.0);
-            int gi = 0;
+            for (int c = 0; c < P; ++c) v[u][c] = (w < clen) ? ldg2_volatile(a.xs[c] + src0 + w) : make_double2(0.0, 0.0);
+        }
 #pragma unroll
-            for (int g = 1; g < P; g <<= 1, ++gi) {
-                s.x = fma(a.hw[gi], v[c ^ g].x, s.x);
-                s.y = fma(a.hw[gi], v[c ^ g].y, s.y);
+        for (int u = 0; u < U; ++u) {
+            const u64 w = w0 + (u64)u * stride;
+            if (w >= clen) continue;
+#pragma unroll
+            for (int c = 0; c < P; ++c) {
+                double2 s = make_double2(0.0, 0.0);
+                int gi = 0;
+#pragma unroll
+                for (int g = 1; g < P; g <<= 1, ++gi) {
+                    s.x = fma(a.hw[gi], v[u][c ^ g].x, s.x);
+                    s.y = fma(a.hw[gi], v[u][c ^ g].y, s.y);
+                }
+                a.z[((u64)c << a.cbits) + w] = s;
             }
-            a.z[((u64)c << a.cbits) + w] = s;
         }
     }
 }

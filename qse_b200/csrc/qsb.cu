@@ -110,7 +110,7 @@ struct qsb_ctx {
     int exchange = -1;                      // option "exchange": -1 auto, 0 direct partner pulls, 1 remap
     int exchange_split = -1;                // option "exchange_split": where the partner tiles are pulled: -1 auto, 0 fused
                                             // launch, 1 half in the fused and half in the last plain launch, 2 plain launch
-    int remap_ctas = 24;                    // option "remap_ctas": SMs the remap kernel takes beside the fused launch
+    int remap_ctas = 32;                    // option "remap_ctas": SMs the remap kernel takes beside the fused launch
     cudaStream_t stream2 = nullptr;         // the remap kernel runs beside the fused launch (sharded contexts)
     cudaEvent_t ev_x = nullptr, ev_z = nullptr;
     // measurement

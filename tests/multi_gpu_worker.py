@@ -60,7 +60,7 @@ def large_shard_cases(rank, world, local, check):
         for k, v in opts.items():
             eng.set_option(k, v)
         y[name] = eng.apply_h(om[11], de[11])
-        for k, v in {"exchange": -1, "exchange_split": -1, "remap_ctas": 24}.items():
+        for k, v in {"exchange": -1, "exchange_split": -1, "remap_ctas": 32}.items():
             eng.set_option(k, v)
     eng.evolve_schedule(om[sel], de[sel], dt[sel])
     evolved = eng.get_state()
@@ -131,12 +131,14 @@ def main():
 
     omega_max = 2 * np.pi
     quick = os.environ.get("QSB_WORKER_QUICK", "0") != "0"  # __graft_entry__.smoke(): one size, peer-memory exchange
-    for exchange in (("ipc",) if quick else ("ipc", "nccl")):
+    modes = tuple(os.environ["QSB_WORKER_MODES"].split(",")) if os.environ.get("QSB_WORKER_MODES") else None
+    sizes = tuple(int(v) for v in os.environ["QSB_WORKER_SIZES"].split(",")) if os.environ.get("QSB_WORKER_SIZES") else None
+    for exchange in (modes or (("ipc",) if quick else ("ipc", "nccl"))):
         if exchange == "nccl":
             os.environ["QSB_NO_IPC"] = "1"
         else:
             os.environ.pop("QSB_NO_IPC", None)
-        for n in ((14,) if quick else (8, 14, 17, 19) if world >= 4 else (8, 14, 17)):
+        for n in (sizes or ((14,) if quick else (8, 14, 17, 19) if world >= 4 else (8, 14, 17))):
             reg = qb.lattices.random_register(n, 0.9 * qb.blockade_radius(omega_max), seed=n)
             plan = qdist.ShardPlan(n, world)
             v = orc.interaction_matrix(reg.positions)

@@ -19,7 +19,7 @@ import qse_b200 as qb
 from qse_b200 import distributed as qdist
 from qse_b200 import lib
 
-DEFAULTS = {"exchange": -1, "exchange_split": -1, "remap_ctas": 24, "sb_bits": 0, "sb_lag": 0}
+DEFAULTS = {"exchange": -1, "exchange_split": -1, "remap_ctas": 32, "sb_bits": 0, "sb_lag": 0}
 
 args = sys.argv[1:]
 local_q = 25
