@@ -33,7 +33,7 @@ extern "C" {
 
 #define QSB_ABI_VERSION 1
 #define QSB_NCCL_UID_BYTES 128
-#define QSB_MAX_QUBITS 40
+#define QSB_MAX_QUBITS 36   /* 33 local qubits + 3 sharded ones (8 ranks) */
 
 typedef struct qsb_ctx qsb_ctx;
 
@@ -58,7 +58,7 @@ int qsb_nccl_unique_id(void* out_uid /* QSB_NCCL_UID_BYTES */);
 /* ---- context ---------------------------------------------------------------------- */
 /* replaces: Qutip.__init__ state set-up (qse/calc/qutip.py:13-32) */
 int qsb_create(int n_qubits, int device, qsb_ctx** out);
-/* [collective] nranks must be a power of two <= 2^n_qubits; nccl_uid from qsb_nccl_unique_id */
+/* [collective] nranks must be 1, 2, 4 or 8 (at most 3 sharded qubits); nccl_uid from qsb_nccl_unique_id */
 int qsb_create_sharded(int n_qubits, int device, int rank, int nranks, const void* nccl_uid,
                        qsb_ctx** out);
 int qsb_destroy(qsb_ctx* ctx);
@@ -71,7 +71,12 @@ int qsb_local_dim(const qsb_ctx* ctx, uint64_t* dim);   /* 2^(N-p) amplitudes in
  * super-blocks, of the first sub-pass over the second inside the fused launch; 0 = auto),
  * "tile_bits" (12 or 11),
  * "tensor_map" (1 = strided tiles fetched with 2-D tensor-map TMA, 0 = one bulk copy per row),
- * "small_kernel" (1 = schedules of <= 12 qubits run in one single-block launch) */
+ * "small_kernel" (1 = schedules of <= 12 qubits run in one single-block launch),
+ * "diag_on_the_fly" (1 = the H psi kernel evaluates the 2-local diagonal itself instead of reading E),
+ * "ticket_batch" (work items claimed per atomic; 0 = auto), "exchange" (-1 auto, 0 = direct partner pulls,
+ * 1 = qubit-remap exchange), "exchange_split" (where partner tiles are pulled: -1 auto, 0 fused launch,
+ * 1 split between the fused and the last plain launch, 2 last plain launch), "remap_ctas" (SMs the remap kernel
+ * takes beside the fused launch; 0 = run it before the fused launch) */
 int qsb_set_option(qsb_ctx* ctx, const char* key, double value);
 
 /* page-locked host memory for state-sized transfers (qsb_get_state / qsb_set_state run at PCIe
@@ -89,6 +94,23 @@ int qsb_host_free(void* ptr);
 int qsb_set_interaction(qsb_ctx* ctx, const double* v);
 /* E_int of this shard (local_dim doubles): the diagonal of ham_int */
 int qsb_get_diagonal(qsb_ctx* ctx, double* out);
+/* Per-site drive and detuning of the reference's headline Hamiltonian (README.md:93-95):
+ *   H = sum_q (omega/2) w_omega[q] X_q - sum_q delta w_delta[q] n_q + interaction (+ operator terms).
+ * N weights each, NULL = all 1 (the global pulse of qse.calc.Qutip, qse/calc/qutip.py:55-58).  They scale every
+ * (omega, delta) passed afterwards: qsb_apply_h, qsb_evolve_*, qsb_energy, QSB_EOP_ENERGY. */
+int qsb_set_site_weights(qsb_ctx* ctx, const double* w_omega, const double* w_delta);
+/* Operator-sum Hamiltonians (qse.Operators: sums of coef * Pauli strings over X, Y, Z, N;
+ * qse/operator/operator.py:38-60, 80-92): H gains sum_t s_t(t) coef_t P_t with s = 1 (channel 0, static),
+ * omega(t) (channel 1) or delta(t) (channel 2) -- qse.calc.Qutip's H = amp*H_amp + det*H_det + H_int with
+ * arbitrary H_amp / H_det, the TFIM of docs/use-cases/time_evo.ipynb, the XY channel of
+ * qse/calc/pulser.py:174-177.  Masks as in qsb_eops (pairwise disjoint).  Static diagonal strings are folded into
+ * the diagonal, single-X / single-N strings into the per-site drive / detuning (the tiled H psi kernels cost the
+ * same); anything else is applied by a generic gather kernel, one pass over the state per H psi.  Replaces any
+ * previous term list; n_terms = 0 clears it.  channel may be NULL (all static).  qsb_set_interaction (zeros for a
+ * pure operator Hamiltonian) must have been called or is implied with V = 0.  [collective] */
+int qsb_set_operator_terms(qsb_ctx* ctx, int64_t n_terms, const double* coef, const uint64_t* xmask,
+                           const uint64_t* ymask, const uint64_t* zmask, const uint64_t* nmask,
+                           const int32_t* channel);
 
 /* ---- state ------------------------------------------------------------------------ */
 /* |0...0>: qp.tensor([qp.fock(2)] * N), qse/calc/qutip.py:35 */
@@ -102,6 +124,9 @@ int qsb_get_state(qsb_ctx* ctx, double* re_im /* local_dim*2 */);
  * [collective] */
 int qsb_apply_h(qsb_ctx* ctx, double omega, double delta);
 int qsb_get_work(qsb_ctx* ctx, double* re_im /* local_dim*2 */);
+/* out <- H(omega, delta) in for a caller-supplied shard (get_hamiltonian(amp, det) * state for any state,
+ * qse/calc/qutip.py:55-58) WITHOUT touching the evolved state psi.  [collective] */
+int qsb_apply_h_to(qsb_ctx* ctx, double omega, double delta, const double* in_re_im, double* out_re_im);
 /* psi <- exp(-i H(omega, delta) dt) psi: one qp.sesolve(H, psi, [0, dt]) call
  * (qse/calc/qutip.py:43-45).  n_hpsi (may be NULL) receives the number of H psi applied.
  * [collective] */
@@ -135,6 +160,12 @@ typedef struct {
  * Re <psi|op_o|psi>.  eops may be NULL.  [collective] */
 int qsb_evolve_schedule(qsb_ctx* ctx, const double* omega, const double* delta, const double* dt_us,
                         int64_t n_steps, const qsb_eops* eops, double* expectations_out);
+
+/* the same loop with PER-SITE signal values: omega_sites / delta_sites are n_steps x N row-major, row s holding
+ * Omega_q and delta_q of step s for q = 0..N-1 (site weights still apply on top).  [collective] */
+int qsb_evolve_schedule_sites(qsb_ctx* ctx, const double* omega_sites, const double* delta_sites,
+                              const double* dt_us, int64_t n_steps, const qsb_eops* eops,
+                              double* expectations_out);
 
 /* ---- observables (qse/magnetic.py, qp.expect) --------------------------------------- */
 int qsb_norm(qsb_ctx* ctx, double* out);                                   /* <psi|psi> [collective] */

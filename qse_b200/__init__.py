@@ -10,10 +10,11 @@ The compute path is hand-written sm_100a CUDA behind the C ABI of ``include/qsb.
 (``qse_b200/libqsb.so``, called through ctypes).  There is no CPU fallback.
 """
 
-from .host import C6, Cell, Qbits, Signal, Signals, blockade_radius, lattices  # noqa: F401
-from .calculator import B200, Hamiltonian, flatten_schedule, interaction_matrix  # noqa: F401
+from .host import C6, Cell, Operator, Operators, Qbits, Signal, Signals, blockade_radius, lattices  # noqa: F401
+from .calculator import B200, Hamiltonian, evolve_operators, flatten_schedule, interaction_matrix, operator_terms  # noqa: F401
 from . import magnetic  # noqa: F401
 
-__all__ = ["B200", "Hamiltonian", "Cell", "Qbits", "Signal", "Signals", "lattices", "blockade_radius",
-           "C6", "magnetic", "interaction_matrix", "flatten_schedule"]
+__all__ = ["B200", "Hamiltonian", "Cell", "Qbits", "Signal", "Signals", "Operator", "Operators", "lattices",
+           "blockade_radius", "C6", "magnetic", "interaction_matrix", "flatten_schedule", "operator_terms",
+           "evolve_operators"]
 __version__ = "0.1.0"

@@ -91,18 +91,21 @@ class Hamiltonian:
         self.detuning = float(detuning)
 
     def diagonal(self) -> np.ndarray:
-        """diag(H) of this rank's shard: E_int[k] - detuning * popcount(k)."""
+        """diag(H) of this rank's shard: E[k] - detuning * sum_q w_q b_q(k) (E holds the interaction and any static
+        diagonal operator strings; w_q are the per-site detuning weights, 1 by default)."""
         eng = self.calc._engine_ready()
+        n = self.calc._nqbits()
         k = np.arange(eng.local_dim, dtype=np.uint64) + np.uint64(eng.rank * eng.local_dim)
-        pop = np.zeros(eng.local_dim, dtype=np.int64)
-        for b in range(self.calc._nqbits()):
-            pop += ((k >> np.uint64(b)) & np.uint64(1)).astype(np.int64)
+        w = self.calc._site_weights()[1]
+        pop = np.zeros(eng.local_dim, dtype=np.float64)
+        for q in range(n):
+            pop += w[q] * ((k >> np.uint64(n - 1 - q)) & np.uint64(1)).astype(np.float64)
         return self.detuning * (-1.0 * pop) + eng.diagonal()
 
     def apply(self, psi) -> np.ndarray:
+        """H psi for a caller-supplied state (this rank's shard); the calculator's evolved state is untouched."""
         eng = self.calc._engine_ready()
-        eng.set_state(np.asarray(psi, dtype=np.complex128).reshape(-1))
-        return eng.apply_h(self.amplitude, self.detuning)
+        return eng.apply_h_to(np.asarray(psi, dtype=np.complex128).reshape(-1), self.amplitude, self.detuning)
 
     def __repr__(self):
         return f"Hamiltonian(amplitude={self.amplitude}, detuning={self.detuning})"
@@ -180,10 +183,44 @@ def _pauli_masks(operator, indices, nqbits):
     return masks["X"], masks["Y"], masks["Z"], masks["N"]
 
 
+def operator_terms(operators, nqbits: int, channel: int = 0):
+    """``qse.Operators`` / ``qse.Operator`` -> [(coef, xmask, ymask, zmask, nmask, channel), ...] for
+    ``Engine.set_operator_terms`` (qubit q <-> index bit N-1-q, Operator.to_qutip order:
+    qse/operator/operator.py:80-92)."""
+    ops = operators.operator_list if hasattr(operators, "operator_list") else [operators]
+    out = []
+    for t in ops:
+        if int(t.nqbits) != int(nqbits):
+            raise Exception("The operators must act on the calculator's number of qubits.")
+        out.append((float(t.coef), *_pauli_masks(t.operator, t.indices, nqbits), int(channel)))
+    return out
+
+
+def evolve_operators(hamiltonian, t_final: float, psi0=None, nqbits: int | None = None, device: int = 0, tol: float = 1e-14):
+    """psi(t_final) = exp(-i H t_final) psi0 for a static operator-sum Hamiltonian -- the
+    ``qutip.sesolve(hamiltonian.to_qutip(), psi0, tlist=[0, t_final])`` idiom of docs/use-cases/time_evo.ipynb,
+    on one GPU.  ``psi0`` defaults to |0...0>; returns the flat (2^N,) complex128 state."""
+    n = int(nqbits if nqbits is not None else hamiltonian.nqbits)
+    with lib.Engine(n, device=device) as eng:
+        eng.set_option("tol", tol)
+        eng.set_interaction(np.zeros((n, n)))
+        eng.set_operator_terms(operator_terms(hamiltonian, n))
+        if psi0 is None:
+            eng.reset_state()
+        else:
+            eng.set_state(np.asarray(psi0, dtype=np.complex128).reshape(-1))
+        eng.evolve_segment(0.0, 0.0, float(t_final))
+        return eng.get_state()
+
+
 class B200(_Base):
     """B200-native state-vector calculator for the Rydberg Hamiltonian
 
-        H = (Omega/2) sum_i X_i - delta sum_i n_i + sum_{i<j} C6/|R_i-R_j|^6 n_i n_j .
+        H = (Omega/2) sum_i X_i - delta sum_i n_i + sum_{i<j} C6/|R_i-R_j|^6 n_i n_j
+
+    and its generalisations: per-site drive and detuning ``Omega_i = w_i Omega(t)``,
+    ``delta_i = v_i delta(t)`` (README.md:93-95) and extra operator terms from ``qse.Operators`` (static, or scaled
+    by the amplitude / detuning signal: the TFIM of docs/use-cases/time_evo.ipynb, XY couplings, ...).
 
     Parameters
     ----------
@@ -198,6 +235,14 @@ class B200(_Base):
         "rk4": its 4-term truncation (classical RK4, one H psi chain per segment).
     tol : float
         Termination threshold on the norm of a Taylor term (default 1e-14).
+    site_amplitude, site_detuning : array_like (N,), optional
+        Per-site weights of the amplitude / detuning signal (default: 1 for every site, the global pulse).
+    hamiltonian : qse.Operators, optional
+        Operator terms added to H: ``hamiltonian`` itself is static; ``hamiltonian_amplitude`` /
+        ``hamiltonian_detuning`` are multiplied by the amplitude / detuning signal value of the step (so
+        ``amp * H_amp + det * H_det + H_static`` generalises qse/calc/qutip.py:55-58).
+    interaction : bool
+        ``False`` drops the C6/r^6 term (a pure operator Hamiltonian on the register).
     distributed : bool | None
         Shard over ``torch.distributed`` ranks; ``None`` = when a process group is up.
     return_state : bool | "shard"
@@ -211,7 +256,9 @@ class B200(_Base):
     c6 = C6  # qse/calc/qutip.py:7, 11
 
     def __init__(self, qbits=None, amplitude=None, detuning=None, *, device=None, method="taylor", tol=1e-14,
-                 distributed=None, return_state=True, compute_spins=True, wtimes=False, label="b200"):
+                 distributed=None, return_state=True, compute_spins=True, wtimes=False, label="b200",
+                 site_amplitude=None, site_detuning=None, hamiltonian=None, hamiltonian_amplitude=None,
+                 hamiltonian_detuning=None, interaction=True):
         ok, why = lib.is_available()
         super().__init__(qbits=qbits, label=label, is_calculator_available=ok,
                          installation_message=INSTALLATION_MESSAGE + (" (" + why + ")" if why else ""))
@@ -230,6 +277,12 @@ class B200(_Base):
         self.return_state = return_state
         self.compute_spins = compute_spins
         self.wtimes = wtimes
+        self.site_amplitude = site_amplitude
+        self.site_detuning = site_detuning
+        self.hamiltonian = hamiltonian
+        self.hamiltonian_amplitude = hamiltonian_amplitude
+        self.hamiltonian_detuning = hamiltonian_detuning
+        self.interaction = bool(interaction)
         self.results = None
         self.metrics = None
         self._statevector = None
@@ -273,11 +326,31 @@ class B200(_Base):
             device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else 0
         return rank, world, device
 
+    def _site_weights(self):
+        n = self._nqbits()
+        out = []
+        for w in (self.site_amplitude, self.site_detuning):
+            w = np.ones(n) if w is None else np.asarray(w, dtype=float).reshape(-1)
+            if w.size != n:
+                raise Exception("site_amplitude / site_detuning must hold one weight per qubit.")
+            out.append(w)
+        return out
+
+    def _operator_terms(self):
+        n = self._nqbits()
+        terms = []
+        for ops, chan in ((self.hamiltonian, 0), (self.hamiltonian_amplitude, 1), (self.hamiltonian_detuning, 2)):
+            if ops is not None:
+                terms += operator_terms(ops, n, chan)
+        return terms
+
     def _engine_ready(self) -> lib.Engine:
-        """(Re)build the device context when the register changed (the reference goes stale)."""
+        """(Re)build the device context when the register or the Hamiltonian changed (the reference goes stale)."""
         n = self._nqbits()
         positions = np.array(self.qbits.positions, dtype=float)
-        key = (n, positions.tobytes(), float(self.c6))
+        w_amp, w_det = self._site_weights()
+        terms = self._operator_terms()
+        key = (n, positions.tobytes(), float(self.c6), w_amp.tobytes(), w_det.tobytes(), repr(terms), self.interaction)
         if self._engine is not None and self._engine_key == key:
             return self._engine
         if self._engine is not None:
@@ -290,7 +363,11 @@ class B200(_Base):
 
             uid = qdist.broadcast_unique_id()
         eng = lib.Engine(n, device=device, rank=rank, nranks=world, nccl_uid=uid)
-        eng.set_interaction(interaction_matrix(positions, self.c6))
+        eng.set_interaction(interaction_matrix(positions, self.c6) if self.interaction else np.zeros((n, n)))
+        if self.site_amplitude is not None or self.site_detuning is not None:
+            eng.set_site_weights(w_amp, w_det)
+        if terms:
+            eng.set_operator_terms(terms)
         self._engine = eng
         self._engine_key = key
         self._statevector = None

@@ -114,6 +114,17 @@ class Qbits:
             d[i, j] = d[j, i] = self.get_distance(i, j)
         return d
 
+    def compute_interaction_hamiltonian(self, distance_func, interaction, tol=1e-8):
+        """``Operators`` with one term ``distance_func(|R_i - R_j|) * interaction_i interaction_j`` per pair i < j,
+        kept iff its magnitude exceeds ``tol`` (qse/qbits.py:1239-1304: the TFIM / XY builders of
+        docs/use-cases/time_evo.ipynb and ssh_model.ipynb)."""
+        terms = []
+        for i, j in itertools.combinations(range(self.nqbits), 2):
+            coef = distance_func(self.get_distance(i, j))
+            if np.abs(coef) > tol:
+                terms.append(Operator(interaction, (i, j), self.nqbits, coef))
+        return Operators(terms)
+
     def repeat(self, reps):
         """Tile the register over its cell; site index = (m0*r1 + m1)*nbasis + b."""
         if self.cell is None:
@@ -128,6 +139,88 @@ class Qbits:
         out = Qbits(np.concatenate(blocks), cell=np.array([r * v for r, v in zip(reps, vecs)]))
         out.shape = tuple(int(s * r) for s, r in zip(self.shape, reps))
         return out
+
+
+class Operator:
+    """One Pauli string ``coef * prod op_q`` over "X", "Y", "Z", "N" (N = diag(0, 1)): the duck-typed subset of
+    ``qse.Operator`` (qse/operator/operator.py:4-60) a calculator reads -- ``operator``, ``indices``, ``nqbits``,
+    ``coef``."""
+
+    def __init__(self, operator, indices, nqbits, coef=1.0):
+        indices = [int(indices)] if isinstance(indices, (int, np.integer)) else [int(i) for i in indices]
+        operator = [operator] * len(indices) if isinstance(operator, str) else list(operator)
+        if any(op not in ("X", "Y", "Z", "N") for op in operator):
+            raise Exception("An operator must be one of 'X', 'Y', 'Z' or 'N'.")
+        if any(i < 0 or i >= nqbits for i in indices):
+            raise Exception("Qubit indices must be between 0 and nqbits-1, inclusive.")
+        if len(indices) != len(operator):
+            raise Exception("The number of passed qubits must equal the number of passed operators.")
+        self.operator, self.indices, self.nqbits, self.coef = operator, indices, int(nqbits), coef
+
+    def copy(self):
+        return Operator(self.operator, self.indices, self.nqbits, self.coef)
+
+    def __mul__(self, k):
+        if not isinstance(k, (int, float)):
+            raise NotImplementedError("Multiplication only supported for scalars.")
+        return Operator(self.operator, self.indices, self.nqbits, self.coef * k)
+
+    __rmul__ = __mul__
+
+    def __repr__(self):
+        return f"{self.coef:.2f} " + " ".join(f"{op}{q}" for op, q in zip(self.operator, self.indices))
+
+
+class Operators:
+    """A sum of :class:`Operator` terms (``qse.Operators``, qse/operator/operators.py:4-30, 80-120)."""
+
+    def __init__(self, operator_list=None):
+        self.operator_list = list(operator_list) if operator_list is not None else []
+        if self.operator_list and not all(op.nqbits == self.operator_list[0].nqbits for op in self.operator_list):
+            raise Exception("All operators in operator_list must act on the same number of qubits.")
+
+    @property
+    def nterms(self) -> int:
+        return len(self.operator_list)
+
+    @property
+    def nqbits(self):
+        return self.operator_list[0].nqbits if self.operator_list else None
+
+    def extend(self, other):
+        if self.nterms and other.nqbits != self.nqbits:
+            raise Exception("other must have the same number of qubits.")
+        if hasattr(other, "operator_list"):
+            self.operator_list += other.operator_list
+        elif hasattr(other, "operator") and hasattr(other, "indices"):
+            self.operator_list += [other]
+        else:
+            raise Exception("other must be Operators or Operator.")
+
+    def copy(self):
+        return Operators(self.operator_list.copy())
+
+    def __add__(self, other):
+        out = self.copy()
+        out.extend(other)
+        return out
+
+    def __iadd__(self, other):
+        self.extend(other)
+        return self
+
+    def __mul__(self, k):
+        if not isinstance(k, (int, float)):
+            raise NotImplementedError("Multiplication only supported for scalars.")
+        return Operators([op * k for op in self.operator_list])
+
+    __rmul__ = __mul__
+
+    def __getitem__(self, i):
+        return self.operator_list[i]
+
+    def __repr__(self):
+        return f"Number of terms: {self.nterms}" + "".join("\n" + repr(op) for op in self.operator_list)
 
 
 class Signal:

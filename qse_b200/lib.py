@@ -62,14 +62,20 @@ SIGNATURES = {
     "qsb_set_option": (C.c_int, [_ctx_p, C.c_char_p, C.c_double]),
     "qsb_set_interaction": (C.c_int, [_ctx_p, _c_double_p]),
     "qsb_get_diagonal": (C.c_int, [_ctx_p, _c_double_p]),
+    "qsb_set_site_weights": (C.c_int, [_ctx_p, _c_double_p, _c_double_p]),
+    "qsb_set_operator_terms": (C.c_int, [_ctx_p, C.c_int64, _c_double_p, _c_u64_p, _c_u64_p, _c_u64_p, _c_u64_p,
+                                         C.POINTER(C.c_int32)]),
     "qsb_reset_state": (C.c_int, [_ctx_p]),
     "qsb_set_state": (C.c_int, [_ctx_p, _c_double_p]),
     "qsb_get_state": (C.c_int, [_ctx_p, _c_double_p]),
     "qsb_apply_h": (C.c_int, [_ctx_p, C.c_double, C.c_double]),
     "qsb_get_work": (C.c_int, [_ctx_p, _c_double_p]),
+    "qsb_apply_h_to": (C.c_int, [_ctx_p, C.c_double, C.c_double, _c_double_p, _c_double_p]),
     "qsb_evolve_segment": (C.c_int, [_ctx_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_int)]),
     "qsb_evolve_schedule": (C.c_int, [_ctx_p, _c_double_p, _c_double_p, _c_double_p, C.c_int64,
                                       C.POINTER(QsbEops), _c_double_p]),
+    "qsb_evolve_schedule_sites": (C.c_int, [_ctx_p, _c_double_p, _c_double_p, _c_double_p, C.c_int64,
+                                            C.POINTER(QsbEops), _c_double_p]),
     "qsb_norm": (C.c_int, [_ctx_p, _c_double_p]),
     "qsb_energy": (C.c_int, [_ctx_p, C.c_double, C.c_double, _c_double_p]),
     "qsb_expect_pauli": (C.c_int, [_ctx_p, C.c_int64, _c_double_p, _c_u64_p, _c_u64_p, _c_u64_p, _c_u64_p,
@@ -239,6 +245,29 @@ class Engine:
             raise ValueError(f"V must be ({self.n}, {self.n})")
         self._check(self._lib.qsb_set_interaction(self._ctx, _dp(v)))
 
+    def set_site_weights(self, w_omega=None, w_delta=None):
+        """Per-site weights of the drive / detuning (README.md:93-95): Omega_q = w_omega[q] * Omega(t), ..."""
+        def arr(w):
+            if w is None:
+                return None
+            w = np.ascontiguousarray(w, dtype=np.float64).reshape(-1)
+            if w.size != self.n:
+                raise ValueError(f"site weights must hold {self.n} values")
+            return w
+        wo, wd = arr(w_omega), arr(w_delta)
+        self._check(self._lib.qsb_set_site_weights(self._ctx, _dp(wo) if wo is not None else None,
+                                                   _dp(wd) if wd is not None else None))
+
+    def set_operator_terms(self, terms):
+        """terms: iterable of (coef, xmask, ymask, zmask, nmask[, channel]); channel 0 static, 1 x amplitude(t),
+        2 x detuning(t).  An empty list clears the operator part of H."""
+        terms = list(terms)
+        coef = np.array([t[0] for t in terms] + [0.0], dtype=np.float64)
+        masks = [np.array([int(t[i]) for t in terms] + [0], dtype=np.uint64) for i in (1, 2, 3, 4)]
+        chan = np.array([int(t[5]) if len(t) > 5 else 0 for t in terms] + [0], dtype=np.int32)
+        self._check(self._lib.qsb_set_operator_terms(self._ctx, len(terms), _dp(coef), *[_up(m) for m in masks],
+                                                     chan.ctypes.data_as(C.POINTER(C.c_int32))))
+
     def diagonal(self) -> np.ndarray:
         out = np.empty(self.local_dim, dtype=np.float64)
         self._check(self._lib.qsb_get_diagonal(self._ctx, _dp(out)))
@@ -267,6 +296,17 @@ class Engine:
         self._check(self._lib.qsb_get_work(self._ctx, out.view(np.float64).ctypes.data_as(_c_double_p)))
         return out
 
+    def apply_h_to(self, psi: np.ndarray, omega: float, delta: float) -> np.ndarray:
+        """H(omega, delta) applied to a caller-supplied shard; the evolved state stays untouched."""
+        psi = np.ascontiguousarray(psi, dtype=np.complex128).reshape(-1)
+        if psi.size != self.local_dim:
+            raise ValueError(f"state shard must hold {self.local_dim} amplitudes")
+        out = np.empty(self.local_dim, dtype=np.complex128)
+        self._check(self._lib.qsb_apply_h_to(self._ctx, float(omega), float(delta),
+                                             psi.view(np.float64).ctypes.data_as(_c_double_p),
+                                             out.view(np.float64).ctypes.data_as(_c_double_p)))
+        return out
+
     def evolve_segment(self, omega: float, delta: float, dt_us: float) -> int:
         n = C.c_int(0)
         self._check(self._lib.qsb_evolve_segment(self._ctx, float(omega), float(delta), float(dt_us), C.byref(n)))
@@ -285,6 +325,23 @@ class Engine:
         out = np.zeros((steps, eops.n_ops), dtype=np.float64)
         self._check(self._lib.qsb_evolve_schedule(self._ctx, _dp(omega), _dp(delta), _dp(dt_us), steps,
                                                   C.byref(eops.struct), _dp(out)))
+        return out
+
+    def evolve_schedule_sites(self, omega_sites, delta_sites, dt_us, eops: "PackedEops | None" = None):
+        """Per-site schedule: omega_sites / delta_sites are (n_steps, N) arrays (row s = the values of step s)."""
+        omega_sites = np.ascontiguousarray(omega_sites, dtype=np.float64)
+        delta_sites = np.ascontiguousarray(delta_sites, dtype=np.float64)
+        dt_us = np.ascontiguousarray(dt_us, dtype=np.float64)
+        steps = dt_us.size
+        if omega_sites.shape != (steps, self.n) or delta_sites.shape != (steps, self.n):
+            raise ValueError(f"omega_sites and delta_sites must be ({steps}, {self.n})")
+        if eops is None or eops.n_ops == 0:
+            self._check(self._lib.qsb_evolve_schedule_sites(self._ctx, _dp(omega_sites), _dp(delta_sites), _dp(dt_us), steps,
+                                                            None, None))
+            return None
+        out = np.zeros((steps, eops.n_ops), dtype=np.float64)
+        self._check(self._lib.qsb_evolve_schedule_sites(self._ctx, _dp(omega_sites), _dp(delta_sites), _dp(dt_us), steps,
+                                                        C.byref(eops.struct), _dp(out)))
         return out
 
     # -- observables -----------------------------------------------------------------------

@@ -182,6 +182,28 @@ def main():
                 owner_p = prob.reshape(world, -1).sum(axis=1)
                 check(f"n={n} sampling across shards", bool(np.max(np.abs(owner_freq - owner_p)) < 6 * np.sqrt(0.25 / shots)
                                                             and np.all(prob[smp] > 0)))
+            if exchange == "ipc" and n >= 14:
+                # generalised H: per-site weights + operator strings that flip, sign and
+                # project on SHARDED qubits (qubit 0 is always sharded), applied to a caller-supplied state
+                rs = np.random.default_rng(5 * n)
+                w_amp, w_det = rs.uniform(0.5, 1.5, n), rs.uniform(-1.0, 1.0, n)
+                ham = reg.compute_interaction_hamiltonian(lambda dd: 2.0 / dd**3, ["X", "X"])
+                ham += reg.compute_interaction_hamiltonian(lambda dd: 2.0 / dd**3, ["Y", "Y"])
+                ham += qb.Operator(["Y", "Z"], [0, n - 1], n, coef=0.8)
+                ham += qb.Operator(["Z", "Z"], [0, 1], n, coef=-0.9)
+                ham += qb.Operator(["N", "X"], [0, 3], n, coef=0.35)
+                ham += qb.Operator("X", 0, n, coef=0.25)
+                eng.set_site_weights(w_amp, w_det)
+                eng.set_operator_terms(qb.operator_terms(ham, n))
+                yg = eng.apply_h_to(psi[sl], 3.1, -2.2)
+                wantg = orc.general_apply(psi, n, e_int=e, hw_sites=0.5 * 3.1 * w_amp, d_sites=-2.2 * w_det,
+                                          terms=orc.operators_as_terms(ham))
+                errg = float(np.max(np.abs(yg - wantg[sl])) / np.max(np.abs(wantg)))
+                check(f"n={n} generalised H psi (site weights + operator strings)", errg <= 1e-13, f"rel err {errg:.2e}")
+                eng.set_operator_terms([])
+                eng.set_site_weights(None, None)
+                y2 = eng.apply_h_to(psi[sl], 3.1, -2.2)
+                check(f"n={n} H restored after clearing the operator terms", float(np.max(np.abs(y2 - want[sl])) / np.max(np.abs(want))) <= 1e-13)
             d = float(np.max(np.abs(eng.number() - orc.get_number_operator(psi, n))))
             check(f"{exchange} n={n} number", d <= 1e-12, f"{d:.2e}")
             check(f"{exchange} n={n} norm", abs(eng.norm() - 1.0) <= 1e-12)
