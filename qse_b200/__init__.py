@@ -12,9 +12,9 @@ The compute path is hand-written sm_100a CUDA behind the C ABI of ``include/qsb.
 
 from .host import C6, Cell, Operator, Operators, Qbits, Signal, Signals, blockade_radius, lattices  # noqa: F401
 from .calculator import B200, Hamiltonian, evolve_operators, flatten_schedule, interaction_matrix, operator_terms  # noqa: F401
-from . import magnetic  # noqa: F401
+from . import magnetic, mis  # noqa: F401
 
 __all__ = ["B200", "Hamiltonian", "Cell", "Qbits", "Signal", "Signals", "Operator", "Operators", "lattices",
-           "blockade_radius", "C6", "magnetic", "interaction_matrix", "flatten_schedule", "operator_terms",
+           "blockade_radius", "C6", "magnetic", "mis", "interaction_matrix", "flatten_schedule", "operator_terms",
            "evolve_operators"]
 __version__ = "0.1.0"

@@ -83,13 +83,37 @@ constexpr bool kPublisher = true;
 enum { kItemFirst = 0, kItemInner = 1, kItemPlain = 2, kItemDone = 3, kItemPeer = 4 };
 
 struct WsItem {
+    // first 128 bytes: the tile's row of the static diagonal table, copied in by the TMA engine (kItemFirst):
+    //   w[b]    = sum over the set index bits h >= TB of the tile base of V(h, b), for tile bit b < TB
+    //   w[12]   = sum over pairs h < h' of set bits of the base of V(h, h')
+    double w[16];
     u64 base;
-    double dhi;    // FIRST: diagonal of the tile base (index bits >= TB and the rank's bits): pairs + single-bit terms
-    double w[12];  // FIRST, diagonal on the fly: w[b] = sum over the set high bits h of the base of V(h, b), tile bit b
+    double dhi;    // FIRST: c0 + sum of lin[h] over the set bits of the base (the time-dependent single-bit part)
     int type;
     int sb;        // super-block of the tile; kItemPeer: which sharded qubit's coefficient applies
     int n_follow;  // sharded state: partner stages (kItemPeer) that follow this tile in the ring
+    int pad;
 };
+constexpr int kTileTabDoubles = 16;  // doubles per tile in the static diagonal table (128 bytes)
+
+// Static part of the on-the-fly diagonal per contiguous tile (see WsItem::w); built once per interaction.
+__global__ void __launch_bounds__(256) tile_table_kernel(double* __restrict__ tab, const double* __restrict__ vbits, int nl, int tb) {
+    const u64 n_tiles = 1ull << (nl - tb);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_tiles * kTileTabDoubles; i += (u64)gridDim.x * blockDim.x) {
+        const u64 tau = i / kTileTabDoubles;
+        const int col = (int)(i % kTileTabDoubles);
+        double acc = 0.0;
+        if (col < tb) {
+            for (u64 rest = tau; rest; rest &= rest - 1ull) acc += vbits[(tb + __ffsll((long long)rest) - 1) * kMaxLocalBits + col];
+        } else if (col == 12) {
+            for (u64 r1 = tau; r1; r1 &= r1 - 1ull) {
+                const int h = tb + __ffsll((long long)r1) - 1;
+                for (u64 r2 = r1 & (r1 - 1ull); r2; r2 &= r2 - 1ull) acc += vbits[h * kMaxLocalBits + tb + __ffsll((long long)r2) - 1];
+            }
+        }
+        tab[i] = acc;
+    }
+}
 
 // ring state a consumer carries into ws_process when partner stages follow the tile it is working on
 struct WsRing {
@@ -125,6 +149,8 @@ struct HpsiWs {
     // global load in front of the flip phase).  otf = 0 reads E from eint (3+-local static strings).
     int otf;
     const double* vbits;          // [kMaxLocalBits][kMaxLocalBits], symmetric, zero diagonal (device)
+    const double* tile_tab;       // [n_tiles][kTileTabDoubles]: static per-tile part (tile_table_kernel)
+    u64 tab_stride;               // kTileTabDoubles, or 0 when every tile shares one all-zero row (stored-E mode)
     double lin[kMaxLocalBits];
     double c0;
     double2 scale;
@@ -298,9 +324,13 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
         for (int b = 0; b < kRegBits; ++b) hr[b] = (C::kRegLo + b >= act_lo) ? p.sp.hw[C::kRegLo + b + gshift] : 0.0;
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) {
+#ifdef QSB_EXP_NOREG
+            double2 a = xv[j];
+#else
             double2 a = make_double2(hr[0] * xv[j ^ 1].x, hr[0] * xv[j ^ 1].y);
             cfma(a, hr[1], xv[j ^ 2]);
             cfma(a, hr[2], xv[j ^ 4]);
+#endif
             if constexpr (FIRST) cfma(a, diag[j], xv[j]);
             v[j] = a;
         }
@@ -399,7 +429,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
     double2* tiles = reinterpret_cast<double2*>(smem_raw);
     __shared__ __align__(8) uint64_t full_bar[C::kStages];
     __shared__ __align__(8) uint64_t empty_bar[C::kStages];
-    __shared__ WsItem desc[C::kStages];
+    __shared__ __align__(16) WsItem desc[C::kStages];
     __shared__ int warps_done[2 * C::kStages];  // by item, not by stage: a stage is released before its tile is published
     // one consumer group: a PUBLISHER warp (one of the producer group's spare warps) turns "all 16 warps have
     // stored their part of a FIRST tile" into the gpu-scope fence + done[] increment, so that no consumer warp
@@ -491,19 +521,20 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                         }
                     }
                 }
+#ifdef QSB_EXP_SKIP_INNER
+                if (type == kItemInner) { --it; continue; }
+#endif
+#ifdef QSB_EXP_SKIP_FIRST
+                if (type == kItemFirst) { --it; continue; }
+#endif
                 // diagonal of a contiguous tile's base (identical for its 2^TB amplitudes), computed while the
                 // stage is still busy: lane b < TB sums V(h, b) over the set high bits h (the single-bit offset of
                 // tile bit b); lane l takes high bit l's own terms, c0 + sum lin[h] + sum_{h<h'} V(h, h')
-                double wl = 0.0, eh = 0.0;
+                // time-dependent single-bit part of a contiguous tile's diagonal: c0 + sum of lin[h] over the set
+                // bits of its base (one lane per bit); the pair part comes from the static table with the tile
+                double eh = 0.0;
                 if (type == kItemFirst) {
-                    const u64 hi = tau;  // base >> TB
-                    if (lane < TB)
-                        for (u64 rest = hi; rest; rest &= rest - 1ull) wl += vs[(TB + __ffsll((long long)rest) - 1) * kMaxLocalBits + lane];
-                    if ((hi >> lane) & 1ull) {
-                        eh = p.lin[TB + lane];
-                        for (u64 rest = hi >> (lane + 1) << (lane + 1); rest; rest &= rest - 1ull)
-                            eh += vs[(TB + lane) * kMaxLocalBits + TB + __ffsll((long long)rest) - 1];
-                    }
+                    if ((tau >> lane) & 1ull) eh = p.lin[TB + lane];
                     eh = warp_sum(eh);
                 }
                 if (use > 0) mbar_wait(&empty_bar[s], (uint32_t)((use - 1) & 1ull));
@@ -567,10 +598,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                 const int sb = (int)(tau / n_a);
                 double2* stage = tiles + (size_t)s * C::kTileW;
                 u64 base;
-                if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)(C::kTileW * sizeof(double2)));
+                if (lane == 0)
+                    mbar_expect_tx(&full_bar[s], (uint32_t)(C::kTileW * sizeof(double2)) +
+                                                     (type == kItemFirst ? (uint32_t)(kTileTabDoubles * sizeof(double)) : 0u));
                 __syncwarp();
                 if (type == kItemFirst) {
                     base = tau << TB;
+                    if (lane == 5) bulk_g2s(&desc[s].w[0], p.tile_tab + tau * p.tab_stride, kTileTabDoubles * sizeof(double), &full_bar[s]);
 #ifndef QSB_WS_COPIES
 #define QSB_WS_COPIES 4
 #endif
@@ -605,15 +639,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                 const int n_follow = (p.n_peer > 0 && type != kItemInner &&
                                       (p.peer_sel == 0 || (int)((base >> p.peer_bit) & 1ull) == (p.peer_sel == 2 ? 1 : 0)))
                                          ? p.n_peer : 0;
-                if (type == kItemFirst) {
-                    if (lane < TB) desc[s].w[lane] = wl;
-                    if (lane == 0) desc[s].dhi = eh + p.c0;
-                    __syncwarp();
-                }
+                if (type == kItemFirst && lane == 0) desc[s].dhi = eh + p.c0;
                 if (lane == 0) {
                     if (type == kItemInner) {
                         // the partial y of this super-block must be complete (all its FIRST tiles stored)
+#ifndef QSB_EXP_NODONE
                         while (ld_acquire_u64(p.done + sb) < p.done_target) __nanosleep(32);  // acquire side of done[]
+#endif
                     }
                     desc[s].base = base;
                     desc[s].type = type;
@@ -690,10 +722,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
             if (type == kItemFirst) {
                 // + the tile-base part: its own terms (dhi) and its coupling to this thread's tile bits (w);
                 // the pairs among the three register bits are warp-uniform table reads
-                double eh = desc[s].dhi + ett;
+                double eh = (desc[s].dhi + desc[s].w[12]) + ett;
+#ifndef QSB_EXP_NODIAG
 #pragma unroll
                 for (int b = 0; b < C::kRegLo; ++b)
                     if ((tg >> b) & 1) eh += desc[s].w[b];
+#endif
                 const double c0 = cross[0] + desc[s].w[C::kRegLo], c1 = cross[1] + desc[s].w[C::kRegLo + 1],
                              c2 = cross[2] + desc[s].w[C::kRegLo + 2];
                 const double p01 = vs[C::kRegLo * kMaxLocalBits + C::kRegLo + 1], p02 = vs[C::kRegLo * kMaxLocalBits + C::kRegLo + 2],
@@ -716,7 +750,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                 // counter; the last warp of the group to finish issues ONE gpu-scope fence (cumulative
                 // over the writes it observed through the counter) and bumps the super-block counter.
                 __syncwarp();
+#ifdef QSB_EXP_NODONE
+                if (false) {
+#else
                 if constexpr (kPublisher && C::kGroups == 1) {
+#endif
                     if (lane == 0) {
                         const int slot = (int)(n_first % kPubSlots);
                         if (warp == 0) {
@@ -727,7 +765,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                         mbar_arrive(&pub_bar[slot]);  // release: this warp's stores precede the publisher's fence
                     }
                     ++n_first;
+#ifdef QSB_EXP_NODONE
+                } else if (false) {
+#else
                 } else if (lane == 0) {
+#endif
                     __threadfence_block();
                     // a warp cannot run more than kStages items ahead of the slowest one: 2 * kStages slots never alias
                     const int slot = (int)(it % (2 * C::kStages));

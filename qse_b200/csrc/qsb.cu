@@ -93,6 +93,8 @@ struct qsb_ctx {
     double dm_c0 = 0.0;
     std::vector<double> dm_lin, dm_pair;
     double* vbits_dev = nullptr;            // dm_pair over the LOCAL index bits, [kMaxLocalBits][kMaxLocalBits]
+    double* tile_tab[2] = {nullptr, nullptr};  // static per-tile part of the diagonal for 2^12 / 2^11-amplitude tiles
+    double* tab_zero = nullptr;             // one all-zero table row (stored-E mode)
     int diag_otf = 1;                       // option "diag_on_the_fly"
     // options
     double tol = 1e-14, theta_max = 3.0;
@@ -415,6 +417,18 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, const HParam
     a.sp = hp.sp;
     a.otf = hp.otf ? 1 : 0;
     a.vbits = c->vbits_dev + (hp.otf ? 0 : kMaxLocalBits * kMaxLocalBits);  // second table: all zero
+    {
+        double*& tab = c->tile_tab[w.tb == 12 ? 0 : 1];
+        if (!tab) {  // built on first use for this tile size, from the current pair table
+            const u64 n = (c->dim >> w.tb) * kTileTabDoubles;
+            CU(cudaMalloc(&tab, n * sizeof(double)));
+            tile_table_kernel<<<grid_for(c, n, 256), 256, 0, c->stream>>>(tab, c->vbits_dev, c->nl, w.tb);
+            LAUNCHED(c);
+            TRY(check_launch(c, "tile_table_kernel"));
+        }
+        a.tile_tab = hp.otf ? tab : c->tab_zero;
+        a.tab_stride = hp.otf ? (u64)kTileTabDoubles : 0ull;
+    }
     memcpy(a.lin, hp.lin, sizeof(a.lin));
     a.c0 = hp.c0;
     // remap exchange: from 4 ranks up, when peer memory is mapped and a chunk holds whole tiles
@@ -1276,6 +1290,9 @@ int qsb_destroy(qsb_ctx* c) {
     cudaFree(c->tickets);
     cudaFree(c->gen_dev);
     cudaFree(c->vbits_dev);
+    cudaFree(c->tile_tab[0]);
+    cudaFree(c->tile_tab[1]);
+    cudaFree(c->tab_zero);
     cudaFree(c->diag_dev);
     cudaFree(c->sched_dev);
     cudaFree(c->sb_done);
@@ -1430,6 +1447,14 @@ static int build_diag_model(qsb_ctx* c) {
             if (bi >= c->nl || bj >= c->nl) continue;
             tab[(size_t)bi * kMaxLocalBits + bj] = tab[(size_t)bj * kMaxLocalBits + bi] = c->dm_pair[(size_t)i * n + j];
         }
+    for (int i = 0; i < 2; ++i) {  // the per-tile tables follow the pair table: rebuilt on next use
+        cudaFree(c->tile_tab[i]);
+        c->tile_tab[i] = nullptr;
+    }
+    if (!c->tab_zero) {
+        CU(cudaMalloc(&c->tab_zero, kTileTabDoubles * sizeof(double)));
+        CU(cudaMemset(c->tab_zero, 0, kTileTabDoubles * sizeof(double)));
+    }
     if (!c->vbits_dev) CU(cudaMalloc(&c->vbits_dev, tab.size() * sizeof(double)));
     CU(cudaMemcpyAsync(c->vbits_dev, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));  // tab is a local
