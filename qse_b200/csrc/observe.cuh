@@ -1,6 +1,7 @@
 // observe.cuh — diagonal builder (K1), Pauli-string reductions (K6), probabilities / top-k (K7).
 #pragma once
 #include "common.cuh"
+#include "hpsi.cuh"
 
 namespace qsb {
 
@@ -166,6 +167,149 @@ __global__ void __launch_bounds__(256) finalize_rows_kernel(const double* part, 
     for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) v += part[(size_t)i * stride + col];
     v = block_sum(v, red);
     if (threadIdx.x == 0) out[col] = v;
+}
+
+// ---- K6 tiled: <X_q>, <Y_q> of every qubit whose index bit is active in a tile pass, all in ONE read ---------
+// qse.magnetic.get_spins (qse/magnetic.py:157-173) pairs every amplitude with its bit-q partner.  With the tile
+// machinery of H psi (hpsi.cuh: a tile of 2^12 amplitudes in shared memory, 8 per thread, register partners for
+// the top three tile bits, XOR-permuted LDS.128 for the others) one pass over the state serves EVERY qubit whose
+// index bit lies in the tile: the contiguous pass covers index bits 0..11 -- and, seeing each amplitude exactly
+// once, the Z-basis marginals <n_q> of ALL qubits and the norm too --, each strided pass up to nine more bits.
+// 25 qubits: 3 reads of the state instead of 1 + 2 * 25.
+//   sx_b = sum_k Re conj(c_k) c_{k^m}       sy_b = sum_k (-1)^{b(k)} (c.x p.y - c.y p.x)     (p = c_{k^m})
+// Output per CTA (row of kSpinsRow doubles): sx[12], sy[12] by TILE bit, then (FIRST) norm, n[tile bits 0..11],
+// n[index bits 12..]; summed over CTAs by finalize_rows_kernel in a fixed order (deterministic).
+constexpr int kSpinsRow = 24 + 1 + 12 + 24;
+template <bool FIRST>
+__global__ void __launch_bounds__(kThreads, 1) spins_tile_kernel(const HpsiPass p, double* __restrict__ part) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2* tiles = reinterpret_cast<double2*>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ double red[32];
+    __shared__ double nh_s[kThreads / 32][24];  // per warp: probability mass by set index bit >= 12 of the tile base
+
+    const int t = threadIdx.x;
+    const int warp = t >> 5, lane = t & 31;
+    const u64 first_tile = blockIdx.x;
+    const u64 stride = gridDim.x;
+    const u64 n_my = (p.n_tiles > first_tile) ? (p.n_tiles - first_tile + stride - 1) / stride : 0;
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+    }
+    if (lane < 24) nh_s[warp][lane] = 0.0;
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s)
+            if ((u64)s < n_my) tile_issue(p, tiles + (size_t)s * kTile, &full_bar[s], first_tile + s * stride);
+    }
+    const int act_lo = FIRST ? 0 : p.lb;
+    double sx[kTileBits], sy[kTileBits];
+#pragma unroll
+    for (int b = 0; b < kTileBits; ++b) sx[b] = sy[b] = 0.0;
+    double ptot = 0.0, pj[kPerThread];
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) pj[j] = 0.0;
+
+    for (u64 i = 0; i < n_my; ++i) {
+        const int s = (int)(i % kStages);
+        const uint32_t parity = (uint32_t)((i / kStages) & 1ull);
+        const double2* ts = tiles + (size_t)s * kTile;
+        mbar_wait(&full_bar[s], parity);
+        double2 xv[kPerThread];
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) xv[j] = ts[t + j * kThreads];
+        // tile bits 9..11: partners are this thread's own registers; the own bit is bit b of j
+#pragma unroll
+        for (int b = 0; b < kRegBits; ++b)
+            if (kSmemBits + b >= act_lo) {
+#pragma unroll
+                for (int j = 0; j < kPerThread; ++j) {
+                    const double2 c = xv[j], q = xv[j ^ (1 << b)];
+                    sx[kSmemBits + b] += c.x * q.x + c.y * q.y;
+                    const double im = c.x * q.y - c.y * q.x;
+                    sy[kSmemBits + b] += ((j >> b) & 1) ? -im : im;
+                }
+            }
+        // tile bits act_lo..8: XOR-permuted shared-memory partners; the own bit is bit b of t
+        for (int b = act_lo; b < kSmemBits; ++b) {
+            const int tb = t ^ (1 << b);
+            const double sg = ((t >> b) & 1) ? -1.0 : 1.0;
+            double ax = 0.0, ay = 0.0;
+#pragma unroll
+            for (int j = 0; j < kPerThread; ++j) {
+                const double2 c = xv[j], q = ts[tb + j * kThreads];
+                ax += c.x * q.x + c.y * q.y;
+                ay += c.x * q.y - c.y * q.x;
+            }
+            // dynamic register index would go to local memory: select with a compile-time loop
+#pragma unroll
+            for (int bb = 0; bb < kSmemBits; ++bb)
+                if (bb == b) {
+                    sx[bb] += ax;
+                    sy[bb] += sg * ay;
+                }
+        }
+        if (FIRST) {
+            double pt = 0.0;
+#pragma unroll
+            for (int j = 0; j < kPerThread; ++j) {
+                const double pk = cnorm2(xv[j]);
+                pj[j] += pk;
+                pt += pk;
+            }
+            ptot += pt;
+            // index bits >= 12 are fixed by the tile: its mass goes to every set one (one lane per bit)
+            const u64 hi = (first_tile + i * stride);
+            pt = warp_sum(pt);
+            if (lane < 24 && ((hi >> lane) & 1ull)) nh_s[warp][lane] += pt;
+        }
+        __syncthreads();  // every thread is done reading stage s
+        if (warp == 0 && i + kStages < n_my)
+            tile_issue(p, tiles + (size_t)s * kTile, &full_bar[s], first_tile + (i + kStages) * stride);
+    }
+    double* row = part + (size_t)blockIdx.x * kSpinsRow;
+    for (int b = 0; b < kTileBits; ++b) {
+        double v = 0.0, w = 0.0;
+#pragma unroll
+        for (int bb = 0; bb < kTileBits; ++bb)
+            if (bb == b) {
+                v = sx[bb];
+                w = sy[bb];
+            }
+        v = block_sum(v, red);
+        w = block_sum(w, red);
+        if (t == 0) {
+            row[b] = v;
+            row[kTileBits + b] = w;
+        }
+    }
+    if (FIRST) {
+        double v = block_sum(ptot, red);
+        if (t == 0) row[24] = v;
+        for (int b = 0; b < kSmemBits; ++b) {
+            v = block_sum(((t >> b) & 1) ? ptot : 0.0, red);
+            if (t == 0) row[25 + b] = v;
+        }
+        for (int b = 0; b < kRegBits; ++b) {
+            double a = 0.0;
+#pragma unroll
+            for (int j = 0; j < kPerThread; ++j)
+                if ((j >> b) & 1) a += pj[j];
+            v = block_sum(a, red);
+            if (t == 0) row[25 + kSmemBits + b] = v;
+        }
+        __syncthreads();
+        if (t < 24) {
+            double a = 0.0;
+            for (int w = 0; w < kThreads / 32; ++w) a += nh_s[w][t];
+            row[37 + t] = a;
+        }
+    } else if (t < 1 + 12 + 24) {
+        row[24 + t] = 0.0;
+    }
 }
 
 // <a|b> = sum conj(a_k) b_k

@@ -64,6 +64,7 @@ struct qsb_ctx {
     unsigned long long ws_epoch = 0;
     int ws_sbits_active = -1;
     int small_kernel = 1;  // option "small_kernel": whole-schedule single-CTA kernel for N <= 12
+    int obs_tiled = 1;     // option "tiled_observables": spins from tile passes (3 reads at 25 qubits) instead of 1 + 2N
     double* sched_dev = nullptr;  // device copy of a schedule (small kernel)
     size_t sched_cap = 0;
     int use_tmap = 1;  // option "tensor_map": 2-D tensor-map TMA for strided tiles (0 = one bulk copy per row)
@@ -1365,6 +1366,8 @@ int qsb_set_option(qsb_ctx* c, const char* key, double value) {
         c->tk_batch = (int)value;
     } else if (!strcmp(key, "diag_on_the_fly")) {
         c->diag_otf = value != 0.0;
+    } else if (!strcmp(key, "tiled_observables")) {
+        c->obs_tiled = value != 0.0;
     } else if (!strcmp(key, "small_kernel")) {
         c->small_kernel = value != 0.0;
     } else if (!strcmp(key, "tensor_map")) {
@@ -1784,10 +1787,94 @@ int qsb_number(qsb_ctx* c, double* out) {
     return marginals(c, nullptr, out);
 }
 
+// <X_q>, <Y_q>, <n_q> of every LOCAL qubit and the norm from one tile pass per group of index bits (observe.cuh):
+// 3 reads of the state at 25 qubits.  loc: [3 * n + 1] partial sums of this shard (sx, sy, n per qubit, then norm).
+static int spins_tiled(qsb_ctx* c, double* loc) {
+    const HpsiPlan plan = make_plan(c->nl, false);
+    const u64 n_tiles = c->dim >> kTileBits;
+    const int grid = (int)std::min<u64>(n_tiles, (u64)c->n_sm);
+    if ((size_t)grid * kSpinsRow > c->part_n || (size_t)plan.n_pass * 64 > c->slots_n) return fail(c, QSB_ERR_STATE, "partials buffer too small");
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(spins_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+        CU(cudaFuncSetAttribute(spins_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+        attr_set = true;
+    }
+    for (int i = 0; i < plan.n_pass; ++i) {
+        HpsiPass a{};
+        a.x = c->psi;
+        a.nl = c->nl;
+        a.lb = plan.pass[i].lb;
+        a.hb = plan.pass[i].hb;
+        a.hb0 = plan.pass[i].hb0;
+        a.n_tiles = n_tiles;
+        if (i == 0) spins_tile_kernel<true><<<grid, kThreads, kTileSmemBytes, c->stream>>>(a, c->part);
+        else spins_tile_kernel<false><<<grid, kThreads, kTileSmemBytes, c->stream>>>(a, c->part);
+        LAUNCHED(c);
+        TRY(check_launch(c, "spins_tile_kernel"));
+        finalize_rows_kernel<<<kSpinsRow, 256, 0, c->stream>>>(c->part, grid, kSpinsRow, c->slots + (size_t)i * 64);
+        LAUNCHED(c);
+        TRY(check_launch(c, "finalize_rows_kernel"));
+    }
+    TRY(fetch_slots(c, 0, (size_t)plan.n_pass * 64));
+    const int n = c->n;
+    for (int i = 0; i < 3 * n + 1; ++i) loc[i] = 0.0;
+    const double* first = c->h_slots;
+    loc[3 * n] = first[24];
+    for (int bit = 0; bit < c->nl; ++bit) {
+        const int q = n - 1 - bit;
+        loc[3 * q + 2] = bit < kTileBits ? first[25 + bit] : first[37 + (bit - kTileBits)];
+    }
+    for (int i = 0; i < plan.n_pass; ++i) {
+        const double* row = c->h_slots + (size_t)i * 64;
+        const int lo = (i == 0) ? 0 : plan.pass[i].lb, shift = (i == 0) ? 0 : plan.pass[i].hb0 - plan.pass[i].lb;
+        for (int b = lo; b < kTileBits; ++b) {
+            const int q = n - 1 - (b + shift);
+            loc[3 * q + 0] = row[b];
+            loc[3 * q + 1] = row[kTileBits + b];
+        }
+    }
+    for (int g = 0; g < c->p; ++g)  // a sharded qubit is set in whole shards
+        if ((c->rank >> g) & 1) loc[3 * (n - 1 - (c->nl + g)) + 2] = loc[3 * n];
+    return QSB_OK;
+}
+
 int qsb_spins(qsb_ctx* c, double* out) {
     if (!c || !out) return fail(c, QSB_ERR_INVALID, "NULL argument");
     CU(cudaSetDevice(c->device));
     const int n = c->n;
+    if (c->plan.tiled && c->obs_tiled && 3 * (size_t)n + 1 <= c->slots_n) {
+        std::vector<double> loc(3 * (size_t)n + 1);
+        TRY(rank_barrier(c));
+        TRY(spins_tiled(c, loc.data()));
+        if (c->nranks > 1) {
+            CU(cudaMemcpyAsync(c->slots, loc.data(), loc.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            TRY(allreduce(c, c->slots, loc.size(), kNcclSum));
+            TRY(fetch_slots(c, 0, loc.size()));
+            for (size_t i = 0; i < loc.size(); ++i) loc[i] = c->h_slots[i];
+        }
+        for (int q = 0; q < n; ++q) {
+            out[3 * q + 0] = loc[3 * q + 0];
+            out[3 * q + 1] = loc[3 * q + 1];
+            out[3 * q + 2] = loc[3 * n] - 2.0 * loc[3 * q + 2];  // sum p (1 - 2 b), qse/magnetic.py:150-155
+        }
+        if (c->p > 0) {
+            // X / Y of the sharded qubits pair amplitudes across shards: the Pauli-string path (peer memory)
+            const int np = c->p;
+            std::vector<u64> xm(2 * np, 0), ym(2 * np, 0), zm(2 * np, 0), nm(2 * np, 0);
+            for (int q = 0; q < np; ++q) {
+                xm[q] = 1ull << (n - 1 - q);
+                ym[np + q] = 1ull << (n - 1 - q);
+            }
+            std::vector<TermResult> res(2 * np, TermResult{0.0, 0.0});
+            TRY(pauli_batch(c, 2 * np, xm.data(), ym.data(), zm.data(), nm.data(), res.data()));
+            for (int q = 0; q < np; ++q) {
+                out[3 * q + 0] = res[q].re;
+                out[3 * q + 1] = res[np + q].re;
+            }
+        }
+        return QSB_OK;
+    }
     double tot = 0.0;
     std::vector<double> num(n);
     TRY(marginals(c, &tot, num.data()));

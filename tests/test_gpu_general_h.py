@@ -167,3 +167,25 @@ def test_topk_on_sparse_states():
         idx, p = eng.topk(8)
         assert list(idx[:3]) == [70000, 5, 200001] and list(idx[3:]) == [0, 1, 2, 3, 4]
         assert np.allclose(p[:3], [0.4096, 0.36, 0.2304], rtol=1e-15) and np.all(p[3:] == 0.0)
+
+
+@pytest.mark.parametrize("n", [12, 13, 17, 21, 22, 24])
+def test_tiled_spins_match_the_per_qubit_path_and_the_oracle(n):
+    """<X_q>, <Y_q>, <Z_q> of all qubits from one tile pass per group of index bits (3 reads of the state at 25
+    qubits) against the per-qubit Pauli-string path (1 + 2N reads) and, where it is affordable, the oracle
+    (qse/magnetic.py:119-176)."""
+    psi = rand_state(n, 500 + n)
+    with lib.Engine(n) as eng:
+        eng.set_interaction(np.zeros((n, n)))
+        eng.set_state(psi)
+        tiled = eng.spins()
+        launches = eng.metrics()["kernel_launches"]
+        eng.set_option("tiled_observables", 0)
+        plain = eng.spins()
+        launches_plain = eng.metrics()["kernel_launches"] - launches
+        number = eng.number()
+    assert np.max(np.abs(tiled - plain)) <= 1e-13
+    assert np.max(np.abs(tiled[:, 2] - (1.0 - 2.0 * number))) <= 1e-13
+    assert launches_plain >= 4 * n  # what the tile passes replace
+    if n <= 17:
+        assert np.max(np.abs(tiled - orc.get_spins(psi, n))) <= 1e-12
