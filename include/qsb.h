@@ -72,8 +72,8 @@ int qsb_local_dim(const qsb_ctx* ctx, uint64_t* dim);   /* 2^(N-p) amplitudes in
  * "tile_bits" (12 or 11),
  * "tensor_map" (1 = strided tiles fetched with 2-D tensor-map TMA, 0 = one bulk copy per row),
  * "small_kernel" (1 = schedules of <= 12 qubits run in one single-block launch),
- * "diag_on_the_fly" (1 = the H psi kernel evaluates the 2-local diagonal itself instead of reading E),
- * "ticket_batch" (work items claimed per atomic; 0 = auto), "exchange" (-1 auto, 0 = direct partner pulls,
+ * "diag_on_the_fly" (1 = the H psi kernel evaluates the 2-local diagonal itself instead of reading E; -1 = auto:
+ * from 26 local qubits), "exchange" (-1 auto, 0 = direct partner pulls,
  * 1 = qubit-remap exchange), "exchange_split" (where partner tiles are pulled: -1 auto, 0 fused launch,
  * 1 split between the fused and the last plain launch, 2 last plain launch), "remap_ctas" (SMs the remap kernel
  * takes beside the fused launch; 0 = run it before the fused launch) */

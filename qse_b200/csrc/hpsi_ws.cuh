@@ -55,6 +55,7 @@ constexpr int kWsRegsLaunch = 96, kWsRegsProducer = 32, kWsRegsConsumer = 112;
 static_assert(4 * (kWsRegsLaunch - kWsRegsProducer) >= kConsumerWarps * (kWsRegsConsumer - kWsRegsLaunch), "setmaxnreg budget");
 #define QSB_STR2(x) #x
 #define QSB_STR(x) QSB_STR2(x)
+
 constexpr size_t kWsSmemBytes = 192 * 1024;            // the tile ring
 
 // Tile geometry.  A tile holds 2^TB amplitudes; a consumer thread owns 8 of them, so a tile is
@@ -73,12 +74,6 @@ struct WsCfg {
     static_assert(kGroups >= 1 && kStages >= 2 && kStages <= 12, "tile size");
 };
 constexpr int kMaxStages = 12;
-constexpr int kPubSlots = 8;
-#ifdef QSB_NO_PUBLISHER
-constexpr bool kPublisher = false;
-#else
-constexpr bool kPublisher = true;
-#endif
 
 enum { kItemFirst = 0, kItemInner = 1, kItemPlain = 2, kItemDone = 3, kItemPeer = 4 };
 
@@ -169,7 +164,6 @@ struct HpsiWs {
     unsigned long long* done;   // per super-block: FIRST tiles completed (cumulative over launches)
     unsigned long long done_target;
     u64 n_tiles;     // tiles per sub-pass (= dim >> TB)
-    int tk_batch;    // tickets claimed per atomic (>= 1)
     int use_tmap;    // strided tiles are fetched with ONE 2-D tensor-map TMA per <= 256 rows
     u64 zero;        // always 0, but only the host knows: (bits & zero) makes an address DEPEND on a value, which
                      // pins a load after the phase that produced the value whatever ptxas would like to hoist
@@ -278,18 +272,16 @@ QSB_DEV void cfma(double2& v, double c, double2 x) {
 // FIRST = contiguous tile (index bits 0..TB-1 + diagonal + peers); otherwise strided rows (bits >= lb).
 // A thread owns tile indices idx = t + j * kGroupThreads (j = 0..7): tile bits [TB-3, TB) are
 // register-only flips, every other active tile bit is a conflict-free LDS.128 at an XOR-permuted
-// address.  Global operands (the partial y; E when the diagonal is not computed on the fly) are
-// requested up front with loads the compiler may not sink and are CONSUMED LAST, after the
-// shared-memory flip phase, so that their L2 / HBM latency hides behind it.
-// Sharded state: n_follow partner stages (kItemPeer) follow the tile in the ring -- the same 2^TB amplitudes
-// of a partner GPU's x (or of a remap buffer), pulled over NVLink by the producer's TMA copies.  They are folded
-// into the accumulators after the flip phase, straight from shared memory: the transfer latency sits in the
-// ring like any other tile load, no consumer ever stalls on an NVLink access and nothing takes a detour
-// through y.
-// diag: FIRST only -- the diagonal of H for this thread's 8 amplitudes.
-template <int TB, bool FIRST, bool LAST>
-QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 base, int t, const double (&diag)[kPerThread],
-                        double& red, uint64_t* empty, const WsRing& ring, int n_follow, u64& it) {
+// address.  Global operands (E or partial y, the first NVLink partner) are requested up front with
+// loads the compiler may not sink, so their latency hides behind the shared-memory flip phase.
+// PEER (FIRST only, sharded state): the producer has already pulled the partner tiles over NVLink
+// (kItemPeer stages, ws_peer below) and y holds sum_g hw_g * partner_g.
+// dsum: FIRST only -- sum of delta_q over the set bits of this thread's index t (bits 0..TB-4) plus
+// the tile's high part (WsItem::dhi).
+template <int TB, bool FIRST, bool LAST, bool SH, bool OTF>
+QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 base, int t, double dsum,
+                        const double (&diag)[kPerThread], double& red, uint64_t* empty, const WsRing& ring, int n_follow,
+                        u64& it) {
     using C = WsCfg<TB>;
     const int lb = FIRST ? TB : p.lb;
     const int hb0 = FIRST ? TB : p.hb0;
@@ -305,14 +297,21 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
     (FIRST ? (u64)((j)*C::kGroupThreads) : (((((u64)((j)*C::kGroupThreads)) >> lb) << hb0) | (((u64)((j)*C::kGroupThreads)) & low_mask)))
 #define QSB_GADDR(j) (g0 + QSB_GOFF(j))
 
-    constexpr bool kHaveY = !FIRST;
-    double2 yv[kHaveY ? kPerThread : 1];
+    double e[FIRST ? kPerThread : 1];
     double2 v[kPerThread];
-    // the partial y (non-FIRST; L2-resident: written by the FIRST tiles of this super-block, or prefetched
-    // by the producer)
-    if constexpr (kHaveY) {
+    if constexpr (FIRST && !OTF) {
 #pragma unroll
-        for (int j = 0; j < kPerThread; ++j) yv[j] = ldcg2(p.y + QSB_GADDR(j));
+        for (int j = 0; j < kPerThread; ++j) e[j] = ldnc1(p.eint + QSB_GADDR(j));
+    }
+    // The accumulators START as the partial y (non-FIRST; L2-resident: written by the FIRST tiles of this
+    // super-block, or prefetched by the producer) or as the partners' term (FIRST + PEER): the loads
+    // land directly in v, there is no second copy to keep (or to spill) through the flip phases.
+    if constexpr (!FIRST) {
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) v[j] = ldcg2(p.y + QSB_GADDR(j));
+    } else {
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) v[j] = make_double2(0.0, 0.0);
     }
     {
         double2 xv[kPerThread];
@@ -324,14 +323,19 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
         for (int b = 0; b < kRegBits; ++b) hr[b] = (C::kRegLo + b >= act_lo) ? p.sp.hw[C::kRegLo + b + gshift] : 0.0;
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) {
-#ifdef QSB_EXP_NOREG
-            double2 a = xv[j];
-#else
+            // the three partner products first, y / zero last: the chain does not wait on the global load
             double2 a = make_double2(hr[0] * xv[j ^ 1].x, hr[0] * xv[j ^ 1].y);
             cfma(a, hr[1], xv[j ^ 2]);
             cfma(a, hr[2], xv[j ^ 4]);
-#endif
-            if constexpr (FIRST) cfma(a, diag[j], xv[j]);
+            if constexpr (FIRST && OTF) {
+                cfma(a, diag[j], xv[j]);  // the 2-local diagonal, evaluated on the fly by the caller
+            } else if constexpr (FIRST) {
+                // diagonal: d = E - sum_q delta_q b_q(k); bits TB-3..TB-1 of the index are j's bits
+                const double dj = ((j & 1) ? p.sp.dl[C::kRegLo] : 0.0) + ((j & 2) ? p.sp.dl[C::kRegLo + 1] : 0.0) +
+                                  ((j & 4) ? p.sp.dl[C::kRegLo + 2] : 0.0);
+                cfma(a, e[j] - (dsum + dj), xv[j]);
+            }
+            if constexpr (!FIRST) cacc(a, v[j]);
             v[j] = a;
         }
     }
@@ -351,17 +355,14 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
             for (int j = 0; j < kPerThread; ++j) cfma(v[j], h, ts[tb + j * C::kGroupThreads]);
         }
     }
-    if constexpr (!LAST) {
+    // SH (sharded state) only: the single-GPU instantiation carries none of this through the flip phase
+    if constexpr (SH && !LAST) {
         // the tile has been read for the last time: hand the stage back to the producer before the stores
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(empty);
     }
-    if constexpr (kHaveY) {
-#pragma unroll
-        for (int j = 0; j < kPerThread; ++j) cacc(v[j], yv[j]);
-    }
-    // partner stages: v += hw_g * partner tile (same tile geometry, so the same shared-memory index)
-    for (int f = 0; f < n_follow; ++f) {
+    // partner stages: v += hw_g * partner tile, same tile geometry, straight from shared memory
+    for (int f = 0; SH && f < n_follow; ++f) {
         it += C::kGroups;
         const int s2 = (int)(it % C::kStages);
         mbar_wait(&ring.full_bar[s2], (uint32_t)((it / C::kStages) & 1ull));
@@ -411,6 +412,8 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
                 p.y[g] = o;
             }
         }
+    }
+    if constexpr (!SH || LAST) {
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(empty);
     }
@@ -419,7 +422,7 @@ QSB_DEV void ws_process(const HpsiWs& p, const double2* __restrict__ ts, u64 bas
 #undef QSB_IDX
 }
 
-template <int TB>
+template <int TB, bool SH, bool OTF>
 __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, const __grid_constant__ CUtensorMap tmap,
                                                                 const __grid_constant__ CUtensorMap tmap_y,
                                                                 const __grid_constant__ CUtensorMap tmap_acc,
@@ -431,21 +434,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
     __shared__ __align__(8) uint64_t empty_bar[C::kStages];
     __shared__ __align__(16) WsItem desc[C::kStages];
     __shared__ int warps_done[2 * C::kStages];  // by item, not by stage: a stage is released before its tile is published
-    // one consumer group: a PUBLISHER warp (one of the producer group's spare warps) turns "all 16 warps have
-    // stored their part of a FIRST tile" into the gpu-scope fence + done[] increment, so that no consumer warp
-    // ever sits in a membar waiting for its stores to drain
-    __shared__ __align__(8) uint64_t pub_bar[kPubSlots];
-    __shared__ int pub_sb[kPubSlots];
-    __shared__ int pub_seq;
     __shared__ double red[32];
     __shared__ int is_last_cta;
-    __shared__ double vs[kMaxLocalBits * kMaxLocalBits];  // pair table of the diagonal, LOCAL index bits
+    __shared__ double pjj[4];  // OTF: pairs among the three register bits of a contiguous tile: (0,1), (0,2), (1,2)
 
     const int t = threadIdx.x;
     const int warp = t >> 5, lane = t & 31;
 
-    if (p.fused) {
-        for (int i = t; i < kMaxLocalBits * kMaxLocalBits; i += kWsThreads) vs[i] = p.vbits[i];
+    if (OTF && p.fused && t < 3) {
+        const int a = (t == 2) ? 1 : 0, b = (t == 0) ? 1 : 2;
+        pjj[t] = p.vbits[(C::kRegLo + a) * kMaxLocalBits + C::kRegLo + b];
     }
     if (t == 0) {
 #pragma unroll
@@ -454,8 +452,6 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
             mbar_init(&empty_bar[s], C::kGroupWarps);
             warps_done[s] = warps_done[s + C::kStages] = 0;
         }
-        for (int q = 0; q < kPubSlots; ++q) mbar_init(&pub_bar[q], kConsumerWarps);
-        pub_seq = 0;
         mbar_fence_init();
     }
     __syncthreads();
@@ -463,7 +459,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
     double part = 0.0;
     if (warp >= kConsumerWarps) {
         // ================= producer warpgroup (only its first warp works) =================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 " QSB_STR(32) ";");  // kWsRegsProducer
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");  // kWsRegsProducer
         if (warp == kConsumerWarps) {
             // Static schedule from ONE global ticket counter.  Tickets enumerate phases of n_a tiles:
             //   A(0) .. A(L-1),  then  A(s), B(s-L)  for s = L .. n_sb-1,  then  B(n_sb-L) .. B(n_sb-1)
@@ -478,67 +474,35 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
             const u64 lag = p.fused ? ((u64)p.lag < n_sb ? (u64)(p.lag < 1 ? 1 : p.lag) : n_sb) : 0;
             const u64 total = p.fused ? 2ull * p.n_tiles : p.n_tiles;
             int n_done = 0;
-            int peer_left = 0;         // partner stages still to publish behind the tile just issued
-            bool pend_first = false;   // ... which was a contiguous (FIRST) tile / a strided one
+            int peer_left = 0;         // partner stages still to publish for the pending FIRST tile
+            bool pend_first = false;   // the tile just issued was a contiguous (FIRST) one / a strided one
             u64 pend_tau = 0;
-            // Tickets are claimed in batches of p.tk_batch with ONE atomic, and the claim of the NEXT batch is
-            // issued when a batch starts: its round trip (~1 us with every SM on the same counter) hides behind
-            // the batch instead of sitting in front of every tile.  Every CTA makes (useful batches + 1) claims,
-            // so the counter ends at a known value and is never reset (ticket_base).  Batches keep the scheme
-            // deadlock-free: a CTA works through its tickets in increasing order, so the lowest unfinished
-            // ticket of the launch is never stuck behind a higher one.
-            const unsigned int tkb = (unsigned int)p.tk_batch;
-            unsigned int pf = 0;
-            if (lane == 0) pf = atomicAdd(p.ticket, tkb) - p.ticket_base;
-            u64 cur = 0;
-            int left = 0;
             for (u64 it = 0;; ++it) {
                 const int s = (int)(it % C::kStages);
                 const u64 use = it / C::kStages;
+                if (use > 0) mbar_wait(&empty_bar[s], (uint32_t)((use - 1) & 1ull));
                 int type = kItemDone;
                 u64 tau = 0;
-                if (peer_left > 0) {
+                if (SH && peer_left > 0) {
                     type = kItemPeer;
                     tau = pend_tau;
                 } else {
-                    if (n_done == 0 && left == 0) {
+                    if (lane == 0 && n_done == 0) {
                         // the counter is never reset: this launch's tickets start at ticket_base (mod 2^32)
-                        const u64 b = (u64)__shfl_sync(0xffffffffu, pf, 0);
-                        if (b < total) {
-                            cur = b;
-                            left = (int)((total - b < (u64)tkb) ? (total - b) : (u64)tkb);
-                            if (lane == 0) pf = atomicAdd(p.ticket, tkb) - p.ticket_base;
+                        const u64 ticket = (u64)(unsigned int)(atomicAdd(p.ticket, 1u) - p.ticket_base);
+                        if (ticket < total) {
+                            if (!p.fused) {
+                                type = kItemPlain;
+                                tau = ticket;
+                            } else {
+                                type = ws_decode_ticket(ticket, n_a, n_sb, lag, (u64)p.sb_xor, &tau);
+                            }
                         }
                     }
-                    if (left > 0) {
-                        const u64 ticket = cur++;
-                        --left;
-                        if (!p.fused) {
-                            type = kItemPlain;
-                            tau = ticket;
-                        } else {
-                            type = ws_decode_ticket(ticket, n_a, n_sb, lag, (u64)p.sb_xor, &tau);
-                        }
-                    }
+                    type = __shfl_sync(0xffffffffu, type, 0);
+                    tau = __shfl_sync(0xffffffffu, tau, 0);
                 }
-#ifdef QSB_EXP_SKIP_INNER
-                if (type == kItemInner) { --it; continue; }
-#endif
-#ifdef QSB_EXP_SKIP_FIRST
-                if (type == kItemFirst) { --it; continue; }
-#endif
-                // diagonal of a contiguous tile's base (identical for its 2^TB amplitudes), computed while the
-                // stage is still busy: lane b < TB sums V(h, b) over the set high bits h (the single-bit offset of
-                // tile bit b); lane l takes high bit l's own terms, c0 + sum lin[h] + sum_{h<h'} V(h, h')
-                // time-dependent single-bit part of a contiguous tile's diagonal: c0 + sum of lin[h] over the set
-                // bits of its base (one lane per bit); the pair part comes from the static table with the tile
-                double eh = 0.0;
-                if (type == kItemFirst) {
-                    if ((tau >> lane) & 1ull) eh = p.lin[TB + lane];
-                    eh = warp_sum(eh);
-                }
-                if (use > 0) mbar_wait(&empty_bar[s], (uint32_t)((use - 1) & 1ull));
-                if (type == kItemPeer) {
+                if (SH && type == kItemPeer) {
                     // partner stage: the SAME amplitudes as the tile just issued, from a partner GPU's x (direct
                     // exchange: one stage per sharded qubit) or from the remap buffers (one stage), pulled over
                     // NVLink by the TMA engine into an ordinary stage of the ring
@@ -600,11 +564,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                 u64 base;
                 if (lane == 0)
                     mbar_expect_tx(&full_bar[s], (uint32_t)(C::kTileW * sizeof(double2)) +
-                                                     (type == kItemFirst ? (uint32_t)(kTileTabDoubles * sizeof(double)) : 0u));
+                                                     ((OTF && type == kItemFirst) ? (uint32_t)(kTileTabDoubles * sizeof(double)) : 0u));
                 __syncwarp();
                 if (type == kItemFirst) {
                     base = tau << TB;
-                    if (lane == 5) bulk_g2s(&desc[s].w[0], p.tile_tab + tau * p.tab_stride, kTileTabDoubles * sizeof(double), &full_bar[s]);
+                    // OTF: the static pair part of the tile's diagonal comes from the per-tile table with the tile
+                    if (OTF && lane == 5) bulk_g2s(&desc[s].w[0], p.tile_tab + tau * p.tab_stride, kTileTabDoubles * sizeof(double), &full_bar[s]);
 #ifndef QSB_WS_COPIES
 #define QSB_WS_COPIES 4
 #endif
@@ -612,7 +577,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                     constexpr int chunk = C::kTileW / kCopies;
                     if (lane < kCopies)
                         bulk_g2s(stage + lane * chunk, p.x + base + (u64)lane * chunk, chunk * sizeof(double2), &full_bar[s]);
-                    if (lane == kCopies && !p.otf) prefetch_l2(p.eint + base, (uint32_t)(C::kTileW * sizeof(double)));
+                    if (!OTF && lane == kCopies) prefetch_l2(p.eint + base, (uint32_t)(C::kTileW * sizeof(double)));
                 } else {
                     base = ws_tile_base(p.lb, p.hb, p.hb0, tau);
                     const int rows = 1 << p.hb;
@@ -636,18 +601,29 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                     }
                 }
                 // does this tile pull its partners in THIS launch?
-                const int n_follow = (p.n_peer > 0 && type != kItemInner &&
+                const int n_follow = (SH && p.n_peer > 0 && type != kItemInner &&
                                       (p.peer_sel == 0 || (int)((base >> p.peer_bit) & 1ull) == (p.peer_sel == 2 ? 1 : 0)))
                                          ? p.n_peer : 0;
-                if (type == kItemFirst && lane == 0) desc[s].dhi = eh + p.c0;
+                double eh = 0.0;
+                if (OTF && type == kItemFirst) {
+                    // time-dependent single-bit part of the tile's diagonal: c0 + sum of lin[h] over the set bits of
+                    // its base, one lane per bit
+                    if ((tau >> lane) & 1ull) eh = p.lin[TB + lane];
+                    eh = warp_sum(eh) + p.c0;
+                }
                 if (lane == 0) {
+                    double dhi = eh;
+                    if (!OTF && type == kItemFirst) {
+                        // detuning of the index bits above the tile (identical for its 2^TB amplitudes)
+                        dhi = p.sp.d_rank;
+                        for (u64 rest = base >> TB; rest; rest &= rest - 1ull) dhi += p.sp.dl[TB + __ffsll((long long)rest) - 1];
+                    }
                     if (type == kItemInner) {
                         // the partial y of this super-block must be complete (all its FIRST tiles stored)
-#ifndef QSB_EXP_NODONE
                         while (ld_acquire_u64(p.done + sb) < p.done_target) __nanosleep(32);  // acquire side of done[]
-#endif
                     }
                     desc[s].base = base;
+                    desc[s].dhi = dhi;
                     desc[s].type = type;
                     desc[s].sb = sb;
                     desc[s].n_follow = n_follow;
@@ -660,116 +636,75 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                 }
                 __syncwarp();
             }
-        } else if (kPublisher && C::kGroups == 1 && warp == kConsumerWarps + 1 && lane == 0 && p.fused) {
-            // ================= publisher (one thread) =================
-            for (unsigned int q = 0;; ++q) {
-                const int slot = (int)(q % kPubSlots);
-                mbar_wait(&pub_bar[slot], (q / kPubSlots) & 1u);  // acquire: all 16 warps have issued their stores
-                const int sb = pub_sb[slot];
-                if (sb < 0) break;
-                __threadfence();  // cumulative gpu-scope release of the tile's stores
-                atomicAdd(p.done + sb, 1ull);
-                *(volatile int*)&pub_seq = (int)(q + 1);
-            }
         }
     } else {
         // ================= consumer warps =================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 " QSB_STR(112) ";");  // kWsRegsConsumer
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");  // kWsRegsConsumer
         const int group = warp / C::kGroupWarps;
         const int tg = t - group * C::kGroupThreads;  // thread index within the group
-        // Diagonal of the amplitudes this thread owns in EVERY contiguous tile, tile-index part: ett = single-bit
-        // terms and pairs among the bits of tg (tile bits 0..TB-4); cross[jb] = single-bit term of register bit jb
-        // (tile bit TB-3+jb) and its pairs with the bits of tg.  Four values per thread for the whole launch.
+        // detuning of the index bits this thread's tile index fixes (bits 0..TB-4 of a FIRST tile)
+        double dlow = 0.0;
+#pragma unroll
+        for (int b = 0; b < C::kRegLo; ++b)
+            if ((tg >> b) & 1) dlow += p.sp.dl[b];
+        // OTF: tile-index part of the diagonal of the amplitudes this thread owns in EVERY contiguous tile: ett =
+        // single-bit terms and pairs among the bits of tg; cross[jb] = single-bit term of register bit jb and its
+        // pairs with the bits of tg.  Four values per thread for the whole launch.
         double ett = 0.0, cross[kRegBits] = {0.0, 0.0, 0.0};
-        if (p.fused) {
+        if (OTF && p.fused) {
 #pragma unroll
             for (int b = 0; b < C::kRegLo; ++b)
                 if ((tg >> b) & 1) {
                     ett += p.lin[b];
                     for (int b2 = b + 1; b2 < C::kRegLo; ++b2)
-                        if ((tg >> b2) & 1) ett += vs[b * kMaxLocalBits + b2];
+                        if ((tg >> b2) & 1) ett += __ldg(p.vbits + b * kMaxLocalBits + b2);
                 }
 #pragma unroll
             for (int jb = 0; jb < kRegBits; ++jb) {
                 double c = p.lin[C::kRegLo + jb];
                 for (int b = 0; b < C::kRegLo; ++b)
-                    if ((tg >> b) & 1) c += vs[b * kMaxLocalBits + C::kRegLo + jb];
+                    if ((tg >> b) & 1) c += __ldg(p.vbits + b * kMaxLocalBits + C::kRegLo + jb);
                 cross[jb] = c;
             }
         }
-        unsigned int n_first = 0;  // contiguous tiles this CTA has processed (publisher sequence number)
         const WsRing ring{tiles, full_bar, empty_bar, desc};
         for (u64 it = (u64)group;; it += C::kGroups) {
             const int s = (int)(it % C::kStages);
             const u64 use = it / C::kStages;
             mbar_wait(&full_bar[s], (uint32_t)(use & 1ull));
             const int type = desc[s].type;
-            if (type == kItemDone) {
-                if (kPublisher && C::kGroups == 1 && p.fused && lane == 0) {  // tell the publisher to stop
-                    const int slot = (int)(n_first % kPubSlots);
-                    if (warp == 0) {
-                        while ((int)n_first - *(volatile int*)&pub_seq >= kPubSlots) __nanosleep(20);
-                        pub_sb[slot] = -1;
-                    }
-                    mbar_arrive(&pub_bar[slot]);
-                }
-                break;
-            }
+            if (type == kItemDone) break;
             const u64 base = desc[s].base;
             const int sb = desc[s].sb;
-            const int n_follow = desc[s].n_follow;
+            const int n_follow = SH ? desc[s].n_follow : 0;
             const double2* ts = tiles + (size_t)s * C::kTileW;
             if (type == kItemFirst) {
-                // + the tile-base part: its own terms (dhi) and its coupling to this thread's tile bits (w);
-                // the pairs among the three register bits are warp-uniform table reads
-                double eh = (desc[s].dhi + desc[s].w[12]) + ett;
-#ifndef QSB_EXP_NODIAG
-#pragma unroll
-                for (int b = 0; b < C::kRegLo; ++b)
-                    if ((tg >> b) & 1) eh += desc[s].w[b];
-#endif
-                const double c0 = cross[0] + desc[s].w[C::kRegLo], c1 = cross[1] + desc[s].w[C::kRegLo + 1],
-                             c2 = cross[2] + desc[s].w[C::kRegLo + 2];
-                const double p01 = vs[C::kRegLo * kMaxLocalBits + C::kRegLo + 1], p02 = vs[C::kRegLo * kMaxLocalBits + C::kRegLo + 2],
-                             p12 = vs[(C::kRegLo + 1) * kMaxLocalBits + C::kRegLo + 2];
+                const double dsum = dlow + desc[s].dhi;
                 double diag[kPerThread];
-                diag[0] = eh;
-                diag[1] = eh + c0;
-                diag[2] = eh + c1;
-                diag[3] = diag[1] + (c1 + p01);
-                diag[4] = eh + c2;
-                diag[5] = diag[4] + (c0 + p02);
-                diag[6] = diag[4] + (c1 + p12);
-                diag[7] = diag[6] + (c0 + (p01 + p02));
-                if (!p.otf) {  // a static diagonal that is not 2-local: the pair table is zero and E comes from memory
+                if constexpr (OTF) {
+                    // + the tile-base part: its own terms (dhi, w[12]) and its coupling to this thread's tile bits (w)
+                    double eh = (desc[s].dhi + desc[s].w[12]) + ett;
 #pragma unroll
-                    for (int j = 0; j < kPerThread; ++j) diag[j] += ldnc1(p.eint + base + tg + j * C::kGroupThreads);
+                    for (int b = 0; b < C::kRegLo; ++b)
+                        if ((tg >> b) & 1) eh += desc[s].w[b];
+                    const double c0 = cross[0] + desc[s].w[C::kRegLo], c1 = cross[1] + desc[s].w[C::kRegLo + 1],
+                                 c2 = cross[2] + desc[s].w[C::kRegLo + 2];
+                    const double p01 = pjj[0], p02 = pjj[1], p12 = pjj[2];
+                    diag[0] = eh;
+                    diag[1] = eh + c0;
+                    diag[2] = eh + c1;
+                    diag[3] = diag[1] + (c1 + p01);
+                    diag[4] = eh + c2;
+                    diag[5] = diag[4] + (c0 + p02);
+                    diag[6] = diag[4] + (c1 + p12);
+                    diag[7] = diag[6] + (c0 + (p01 + p02));
                 }
-                ws_process<TB, true, false>(p, ts, base, tg, diag, part, &empty_bar[s], ring, n_follow, it);
+                ws_process<TB, true, false, SH, OTF>(p, ts, base, tg, dsum, diag, part, &empty_bar[s], ring, n_follow, it);
                 // publish this tile of partial y: warp barrier -> cta-scope release on the shared
                 // counter; the last warp of the group to finish issues ONE gpu-scope fence (cumulative
                 // over the writes it observed through the counter) and bumps the super-block counter.
                 __syncwarp();
-#ifdef QSB_EXP_NODONE
-                if (false) {
-#else
-                if constexpr (kPublisher && C::kGroups == 1) {
-#endif
-                    if (lane == 0) {
-                        const int slot = (int)(n_first % kPubSlots);
-                        if (warp == 0) {
-                            // the slot's previous use must have been published (the publisher is never that far behind)
-                            while ((int)n_first - *(volatile int*)&pub_seq >= kPubSlots) __nanosleep(20);
-                            pub_sb[slot] = sb;
-                        }
-                        mbar_arrive(&pub_bar[slot]);  // release: this warp's stores precede the publisher's fence
-                    }
-                    ++n_first;
-#ifdef QSB_EXP_NODONE
-                } else if (false) {
-#else
-                } else if (lane == 0) {
-#endif
+                if (lane == 0) {
                     __threadfence_block();
                     // a warp cannot run more than kStages items ahead of the slowest one: 2 * kStages slots never alias
                     const int slot = (int)(it % (2 * C::kStages));
@@ -782,8 +717,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
                 }
             } else {
                 const double nodiag[kPerThread] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                if (p.last) ws_process<TB, false, true>(p, ts, base, tg, nodiag, part, &empty_bar[s], ring, n_follow, it);
-                else ws_process<TB, false, false>(p, ts, base, tg, nodiag, part, &empty_bar[s], ring, n_follow, it);
+                if (p.last) ws_process<TB, false, true, SH, OTF>(p, ts, base, tg, 0.0, nodiag, part, &empty_bar[s], ring, n_follow, it);
+                else ws_process<TB, false, false, SH, OTF>(p, ts, base, tg, 0.0, nodiag, part, &empty_bar[s], ring, n_follow, it);
             }
         }
     }

@@ -54,7 +54,6 @@ struct qsb_ctx {
     // warp-specialised super-block path (hpsi_ws.cuh)
     int path = 0;       // 0 auto (ws when N_local >= 13), 1 untiled, 2 one launch per tile-bit group
     int sb_lag = 0;     // lead of the FIRST tiles over the INNER tiles of the fused launch, in super-blocks
-    int tk_batch = 0;   // option "ticket_batch": work items claimed per atomic (0 = auto)
     int ws_tile_bits = 12;  // 12 (64 KiB tiles, 3 stages; measured best) or 11 (32 KiB tiles, 6 stages, two groups); 0 = fewest launches
     int sb_bits = 0;   // log2 of the L2-resident super-block (10 MiB each; 18 / lead 3 measured best on B200)
     unsigned int* tickets = nullptr;        // one work counter per launch of an H psi (never reset: see ticket_base)
@@ -96,7 +95,7 @@ struct qsb_ctx {
     double* vbits_dev = nullptr;            // dm_pair over the LOCAL index bits, [kMaxLocalBits][kMaxLocalBits]
     double* tile_tab[2] = {nullptr, nullptr};  // static per-tile part of the diagonal for 2^12 / 2^11-amplitude tiles
     double* tab_zero = nullptr;             // one all-zero table row (stored-E mode)
-    int diag_otf = 1;                       // option "diag_on_the_fly"
+    int diag_otf = -1;                      // option "diag_on_the_fly": -1 auto (from 26 local qubits), 0 stored E, 1 on the fly
     // options
     double tol = 1e-14, theta_max = 3.0;
     int max_terms = 64, fixed_terms = 0, force_flat = 0;
@@ -346,7 +345,9 @@ static HParams hparams_from_sites(const qsb_ctx* c, const double* hw_site, const
     h.chan[1] = amp;
     h.chan[2] = det;
     // diagonal model: detuning, plus (on the fly) the static 1- / 2-local part with this rank's bits folded in
-    h.otf = c->diag_otf && c->dm_ok;
+    // measured (same box, tools/ab_hpsi.py): on the fly is 1.3 % slower at 25 qubits, 2.8 % (H psi) / 4.7 % (sweep step)
+    // faster at 28, where the E stream competes with two state-sized streams per pass
+    h.otf = c->dm_ok && (c->diag_otf < 0 ? c->nl >= 26 : c->diag_otf != 0);
     memset(h.lin, 0, sizeof(h.lin));
     h.c0 = -h.sp.d_rank;
     for (int b = 0; b < c->nl; ++b) h.lin[b] = -h.sp.dl[b];
@@ -392,17 +393,14 @@ static HParams hparams_rows(const qsb_ctx* c, const double* omega_q, const doubl
     return hparams_from_sites(c, hw, d, amp, det);
 }
 
-// Work items per claim.  Measured (tools/ab_opts.py, 25 / 28 qubits): batches WIDEN the window of super-blocks in
-// flight (148 CTAs x batch tickets) beyond what the L2 holds and what the A -> B lead covers -- 0.70 / 0.74 /
-// 0.94 / 1.24 ms for batches of 1 / 2 / 4 / 8.  One ticket per claim; the claim of the next ticket is issued
-// when the current one is taken, which hides the round trip just as well.
-static int auto_ticket_batch(u64, int) { return 1; }
-static unsigned int take_tickets(qsb_ctx* c, int counter, u64 total, int grid, int batch) {
-    // every launch advances its counter by exactly batch * (ceil(total / batch) + grid): the useful claims plus
-    // one over-the-end claim per CTA (hpsi_ws.cuh, producer warp)
+// Tickets are claimed ONE at a time, right when a stage is free.  Measured (same box, tools/ab_hpsi.py, 25 qubits):
+// claiming in batches of 2 / 4 / 8 costs +6 / +34 / +77 %, and claiming the next ticket ahead of the stage wait +6 %:
+// both widen the window of super-blocks in flight (148 CTAs x tickets held) beyond what the L2 keeps resident and the
+// A -> B lead covers.
+static unsigned int take_tickets(qsb_ctx* c, int counter, u64 total, int grid) {
+    // every launch performs exactly total + grid atomicAdds on its counter (one over-the-end ticket per CTA)
     const unsigned int base = c->ticket_base[counter];
-    const u64 claims = (total + (u64)batch - 1) / (u64)batch + (u64)grid;
-    c->ticket_base[counter] = (unsigned int)(base + (unsigned int)(claims * (u64)batch));
+    c->ticket_base[counter] = (unsigned int)(base + (unsigned int)total + (unsigned int)grid);
     return base;
 }
 
@@ -534,11 +532,7 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, const HParam
         a.red_out = reduce ? red_slot : nullptr;
         a.tail = c->tail;
         a.ticket = c->tickets + i;
-        {
-            const u64 total = a.fused ? 2 * n_tiles : n_tiles;
-            a.tk_batch = c->tk_batch > 0 ? c->tk_batch : auto_ticket_batch(total, lgrid);
-            a.ticket_base = take_tickets(c, i, total, lgrid, a.tk_batch);
-        }
+        a.ticket_base = take_tickets(c, i, a.fused ? 2 * n_tiles : n_tiles, lgrid);
         if (i == 0) {
             if (c->ws_sbits_active != w.sbits * 16 + w.tb) {
                 // the counters are cumulative per super-block: a new block size starts a new count
@@ -584,8 +578,18 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, const HParam
                 }
             }
         }
-        if (w.tb == 11) hpsi_ws_kernel<11><<<lgrid, kWsThreads, kWsSmemBytes, c->stream>>>(a, *tm, *tm_y, *tm_acc, pm);
-        else hpsi_ws_kernel<12><<<lgrid, kWsThreads, kWsSmemBytes, c->stream>>>(a, *tm, *tm_y, *tm_acc, pm);
+#define QSB_WS_LAUNCH(TB_, SH_, OTF_) hpsi_ws_kernel<TB_, SH_, OTF_><<<lgrid, kWsThreads, kWsSmemBytes, c->stream>>>(a, *tm, *tm_y, *tm_acc, pm)
+        if (w.tb == 11) {
+            if (hp.otf) QSB_WS_LAUNCH(11, false, true);
+            else QSB_WS_LAUNCH(11, false, false);
+        } else if (c->nranks == 1) {
+            if (hp.otf) QSB_WS_LAUNCH(12, false, true);
+            else QSB_WS_LAUNCH(12, false, false);
+        } else {
+            if (hp.otf) QSB_WS_LAUNCH(12, true, true);
+            else QSB_WS_LAUNCH(12, true, false);
+        }
+#undef QSB_WS_LAUNCH
         LAUNCHED(c);
         TRY(check_launch(c, "hpsi_ws_kernel"));
     }
@@ -1230,8 +1234,12 @@ int qsb_create_sharded(int n_qubits, int device, int rank, int nranks, const voi
         CUB(cudaFuncSetAttribute(hpsi_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
         CUB(cudaFuncSetAttribute(hpsi_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
         CUB(cudaFuncSetAttribute(hpsi_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
-        CUB(cudaFuncSetAttribute(hpsi_ws_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes));
-        CUB(cudaFuncSetAttribute(hpsi_ws_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes));
+        CUB(cudaFuncSetAttribute(hpsi_ws_kernel<11, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes));
+        CUB(cudaFuncSetAttribute(hpsi_ws_kernel<11, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes));
+        CUB(cudaFuncSetAttribute(hpsi_ws_kernel<12, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes));
+        CUB(cudaFuncSetAttribute(hpsi_ws_kernel<12, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes));
+        CUB(cudaFuncSetAttribute(hpsi_ws_kernel<12, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes));
+        CUB(cudaFuncSetAttribute(hpsi_ws_kernel<12, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsSmemBytes));
         CUB(cudaMalloc(&c->tickets, 17 * sizeof(unsigned int)));
         CUB(cudaMemset(c->tickets, 0, 17 * sizeof(unsigned int)));
         c->tail = c->tickets + 16;
@@ -1362,10 +1370,10 @@ int qsb_set_option(qsb_ctx* c, const char* key, double value) {
         if (value < 0 || value > 128) return fail(c, QSB_ERR_INVALID, "remap_ctas must be in 0..128");
         c->remap_ctas = (int)value;
     } else if (!strcmp(key, "ticket_batch")) {
-        if (value < 0 || value > 64) return fail(c, QSB_ERR_INVALID, "ticket_batch must be 0 (auto) or in 1..64");
-        c->tk_batch = (int)value;
+        if (value != 0.0 && value != 1.0) return fail(c, QSB_ERR_INVALID, "ticket_batch: only 1 (or 0 = auto) is supported; batches were measured slower");
     } else if (!strcmp(key, "diag_on_the_fly")) {
-        c->diag_otf = value != 0.0;
+        if (value != -1.0 && value != 0.0 && value != 1.0) return fail(c, QSB_ERR_INVALID, "diag_on_the_fly must be -1, 0 or 1");
+        c->diag_otf = (int)value;
     } else if (!strcmp(key, "tiled_observables")) {
         c->obs_tiled = value != 0.0;
     } else if (!strcmp(key, "small_kernel")) {

@@ -31,6 +31,8 @@ def child(n):
             eng.set_option("tensor_map", int(os.environ["QSB_TMAP"]))
         if os.environ.get("QSB_TB"):
             eng.set_option("tile_bits", int(os.environ["QSB_TB"]))
+        for kv in filter(None, os.environ.get("QSB_OPTS", "").split(",")):  # any qsb_set_option key=value
+            eng.set_option(kv.split("=")[0], float(kv.split("=")[1]))
         eng.reset_state()
         eng.evolve_schedule(np.full(2, 3.0), np.full(2, -4.0), np.full(2, 0.001))
         ms = eng.time_apply_h(3.0, -4.0, 14, False)[4:]

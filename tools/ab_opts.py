@@ -16,7 +16,7 @@ import numpy as np
 import qse_b200 as qb
 from qse_b200 import lib
 
-DEFAULTS = {"diag_on_the_fly": 1, "ticket_batch": 0, "sb_bits": 0, "sb_lag": 0, "tile_bits": 12, "tensor_map": 1, "hpsi_path": 0}
+DEFAULTS = {"diag_on_the_fly": -1, "sb_bits": 0, "sb_lag": 0, "tile_bits": 12, "tensor_map": 1, "hpsi_path": 0}
 
 n = int(sys.argv[1])
 sets = [dict((kv.split("=")[0], float(kv.split("=")[1])) for kv in a.split(",")) for a in sys.argv[2:]] or [{}]
