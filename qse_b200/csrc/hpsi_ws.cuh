@@ -13,8 +13,12 @@
 //     UTMALDG) for strided tiles -- issues L2 prefetches for the operands the consumers read with
 //     plain loads, and publishes each stage on a "full" mbarrier; 16 consumer warps process tiles
 //     and release stages through "empty" mbarriers.  No __syncthreads in the steady state.
-//   * sharded state: partner tiles (or, from 4 ranks up, tiles of the partners' remap buffers) are
-//     pulled over NVLink by the same producer with the same bulk copies (kItemPeer stages).
+//   * sharded state (template parameter SH): behind a tile the same producer pulls the SAME amplitudes of the
+//     partners' x (or, from 4 ranks up, of the remap buffers) over NVLink into ordinary stages (kItemPeer:
+//     bulk copies for contiguous tiles, tensor-map boxes on the peer pointers for strided ones) and the
+//     consumers fold them into the accumulators from shared memory after the flip phase.  Which tiles pull
+//     in which launch is the host's choice (peer_sel): the NVLink traffic runs beside ALL local work.
+//   * diagonal on the fly (template parameter OTF): no E array is read; see HpsiWs::otf.
 //   * a FUSED launch covers the low `sbits` index bits in two sub-passes that share one trip to
 //     HBM: a super-block of 2^sbits amplitudes (x 16 B + y 16 B + E 8 B per amplitude) fits in the
 //     126 MB L2, so sub-pass B (index bits 12..sbits-1, strided rows) re-reads x and the partial
@@ -35,7 +39,10 @@
 // coefficient coming straight from the constant bank -- a per-site drive costs exactly what the
 // global one does.  The accumulators (8 amplitudes = 32 registers) are the only state a thread
 // carries through the shared-memory flip phase, which leaves room for eight 16-byte loads in
-// flight per thread and no spills (round 1 carried sum + x + y = 96 registers and spilled y).
+// flight per thread (round 1 carried sum + x + y = 96 registers and spilled y).  The kernel is bound by
+// the L1 / shared-memory data pipe (ncu: 74 % busy), so anything that adds traffic to that pipe --
+// spills, a second copy of y, more static shared memory (a smaller L1 carve-out) -- costs time
+// one for one: see the tuning log in DESIGN.md before changing the consumer loop.
 #pragma once
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
