@@ -970,6 +970,17 @@ static int pauli_batch(qsb_ctx* c, int64_t n_terms, const u64* xm, const u64* ym
             a.nl = c->nl;
             a.part = c->part;
             sign[(size_t)t] = (__builtin_popcountll(rank & zz_g) & 1) ? -1.0 : 1.0;  // sharded Z / Y bits
+            if (mode == 1 && __builtin_popcountll(a.flip) == 2 && c->nl >= 2) {
+                // XX + YY of a local pair: the quarter-space pair kernel (each contributing amplitude read once)
+                const int bi = __builtin_ctzll(a.flip), bj = 63 - __builtin_clzll(a.flip);
+                xxyy_pair_kernel<<<std::min(grid, grid_for(c, c->dim >> 2, 256)), 256, 0, c->stream>>>(c->psi, c->nl, bi, bj, c->part);
+                LAUNCHED(c);
+                TRY(check_launch(c, "xxyy_pair_kernel"));
+                finalize_pair_kernel<<<1, 256, 0, c->stream>>>(c->part, std::min(grid, grid_for(c, c->dim >> 2, 256)), c->slots + 2 * t);
+                LAUNCHED(c);
+                TRY(check_launch(c, "finalize_pair_kernel"));
+                continue;
+            }
             pauli_kernel<<<grid, 256, 0, c->stream>>>(a);
             LAUNCHED(c);
             TRY(check_launch(c, "pauli_kernel"));
