@@ -68,7 +68,7 @@ int qsb_local_dim(const qsb_ctx* ctx, uint64_t* dim);   /* 2^(N-p) amplitudes in
  * 4 = classical RK4), "hpsi_path" (0 auto = warp-specialised super-block kernel, 1 = untiled
  * one-thread-per-amplitude kernel, 2 = one launch per tile-bit group), "sb_bits" (log2 of the
  * L2-resident super-block, 13..21; 0 = auto: 18..21 by shard size), "sb_lag" (lead, in
- * super-blocks, of the first sub-pass over the second inside the fused launch; 0 = auto),
+ * super-blocks, of the first sub-pass over the second inside the fused launch; 0 = auto, -1 = no lead),
  * "tile_bits" (12 or 11),
  * "tensor_map" (1 = strided tiles fetched with 2-D tensor-map TMA, 0 = one bulk copy per row),
  * "small_kernel" (1 = schedules of <= 12 qubits run in one single-block launch),

@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) hpsi_ws_kernel(const HpsiWs p, 
             // trips per item put the producer on the critical path.)
             const u64 n_a = p.fused ? (1ull << (p.sbits - TB)) : 1;  // tiles per super-block
             const u64 n_sb = p.fused ? (p.n_tiles / n_a) : 0;
-            const u64 lag = p.fused ? ((u64)p.lag < n_sb ? (u64)(p.lag < 1 ? 1 : p.lag) : n_sb) : 0;
+            const u64 lag = p.fused ? ((u64)(p.lag < 0 ? 0 : p.lag) < n_sb ? (u64)(p.lag < 0 ? 0 : p.lag) : n_sb) : 0;  // 0: B(s) right after A(s)
             const u64 total = p.fused ? 2ull * p.n_tiles : p.n_tiles;
             int n_done = 0;
             int peer_left = 0;         // partner stages still to publish for the pending FIRST tile

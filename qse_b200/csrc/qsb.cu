@@ -256,7 +256,9 @@ static WsPlan make_ws_plan_tb(int nl, int sb_bits, int tb) {
 // Up to 21 local qubits the whole shard is ONE super-block (a single fused launch, measured faster:
 // 19/20/21 qubits 22/31/51 us against 28/39/63 us with a plain launch on top).
 static int auto_sb_bits(int nl) { return nl <= 21 ? nl : std::max(18, std::min(21, nl - 9)); }
-static int auto_sb_lag(int sbits) { return sbits <= 18 ? 3 : (sbits == 19 ? 2 : 1); }
+// 2^21-amplitude blocks (30 local qubits) hold 64 MiB of x + y each: with any lead two of them are in flight and the
+// second sub-pass re-reads x and y from HBM (ncu: 80.5 instead of 40 B/amp); lead 0 hands out B(s) right after A(s).
+static int auto_sb_lag(int sbits) { return sbits <= 18 ? 3 : (sbits == 19 ? 2 : (sbits == 20 ? 1 : 0)); }
 
 static WsPlan make_ws_plan(int nl, int sb_bits, int tile_bits) {
     if (sb_bits == 0) sb_bits = auto_sb_bits(nl);
@@ -505,7 +507,7 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, const HParam
         a.hb = g.hb;
         a.hb0 = g.hb0;
         a.last = (last && fuse) ? 1 : 0;
-        a.lag = c->sb_lag > 0 ? c->sb_lag : auto_sb_lag(w.sbits);
+        a.lag = c->sb_lag > 0 ? c->sb_lag : (c->sb_lag < 0 ? 0 : auto_sb_lag(w.sbits));
         // partner stages of this launch
         if (i == 0) {
             a.n_peer = (split == 2) ? 0 : np;
@@ -1395,7 +1397,7 @@ int qsb_set_option(qsb_ctx* c, const char* key, double value) {
         if (value != 0.0 && value != 11.0 && value != 12.0) return fail(c, QSB_ERR_INVALID, "tile_bits must be 0, 11 or 12");
         c->ws_tile_bits = (int)value;
     } else if (!strcmp(key, "sb_lag")) {
-        if (value < 0 || value > 64) return fail(c, QSB_ERR_INVALID, "sb_lag must be in 0..64");
+        if (value < -1 || value > 64) return fail(c, QSB_ERR_INVALID, "sb_lag must be -1 (no lead), 0 (auto) or in 1..64");
         c->sb_lag = (int)value;
     } else if (!strcmp(key, "sb_bits")) {
         if (value != 0.0 && (value < 13 || value > 21)) return fail(c, QSB_ERR_INVALID, "sb_bits must be 0 (auto) or in 13..21");
@@ -2228,7 +2230,7 @@ int qsb_describe_plan(int n_local, int sb_bits, int tile_bits, int* out) {
 int qsb_describe_ticket(uint64_t ticket, uint64_t n_a, uint64_t n_sb, uint64_t lag, uint64_t sb_xor, int* type,
                         uint64_t* tile) {
     qsb_ctx* c = nullptr;
-    if (!type || !tile || n_a == 0 || n_sb == 0 || lag == 0 || lag > n_sb || ticket >= 2 * n_a * n_sb || sb_xor >= n_sb)
+    if (!type || !tile || n_a == 0 || n_sb == 0 || lag > n_sb || ticket >= 2 * n_a * n_sb || sb_xor >= n_sb)
         return fail(c, QSB_ERR_INVALID, "bad schedule parameters");
     u64 tau = 0;
     *type = ws_decode_ticket(ticket, n_a, n_sb, lag, sb_xor, &tau);

@@ -113,6 +113,10 @@ def test_super_block_schedules(n, sb):
         for _ in range(3):
             got = eng.apply_h(4.0, 2.5)
             assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+        eng.set_option("sb_lag", -1)  # no lead: B(s) handed out right after A(s) (the 30-qubit schedule)
+        got = eng.apply_h(4.0, 2.5)
+        assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+        eng.set_option("sb_lag", 0)
         # changing the block size mid-life restarts the completion counters
         eng.set_option("sb_bits", 13 if sb != 13 else 14)
         got = eng.apply_h(4.0, 2.5)

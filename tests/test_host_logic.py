@@ -122,7 +122,8 @@ def test_hpsi_launch_plan_covers_every_qubit_once(tile_bits, sb_bits):
             assert len(plan["plain"]) == (0 if nl <= 21 else 1 if nl <= 30 else 2)
 
 
-@pytest.mark.parametrize("n_sb,n_a,lag,sb_xor", [(1, 4, 1, 0), (2, 8, 1, 0), (8, 4, 3, 0), (8, 4, 8, 5), (16, 2, 2, 12), (32, 1, 3, 7)])
+@pytest.mark.parametrize("n_sb,n_a,lag,sb_xor", [(1, 4, 1, 0), (2, 8, 1, 0), (8, 4, 3, 0), (8, 4, 8, 5), (16, 2, 2, 12), (32, 1, 3, 7),
+                                                 (8, 4, 0, 0), (4, 2, 0, 3), (1, 4, 0, 0)])
 def test_fused_launch_schedule_invariants(n_sb, n_a, lag, sb_xor):
     """The ticket order the producer warps follow (evaluated on the host through the C ABI): every
     (sub-pass, tile) is handed out exactly once, and every INNER tile of a super-block comes after ALL
@@ -149,5 +150,5 @@ def test_fused_launch_schedule_invariants(n_sb, n_a, lag, sb_xor):
     for sb in range(n_sb):
         assert first_inner[sb] > last_first[sb]
         gap = first_inner[sb] - last_first[sb] - 1
-        assert gap >= (min(lag, n_sb) - 1) * n_a - (n_a if sb >= n_sb - lag else 0) or n_sb <= lag
+        assert gap >= max(0, (min(lag, n_sb) - 1) * n_a - (n_a if sb >= n_sb - lag else 0)) or n_sb <= lag
     assert dll.qsb_describe_ticket(2 * n_a * n_sb, n_a, n_sb, lag, sb_xor, ctypes.byref(kind), ctypes.byref(tile)) == -1
