@@ -95,7 +95,7 @@ struct qsb_ctx {
     double* vbits_dev = nullptr;            // dm_pair over the LOCAL index bits, [kMaxLocalBits][kMaxLocalBits]
     double* tile_tab[2] = {nullptr, nullptr};  // static per-tile part of the diagonal for 2^12 / 2^11-amplitude tiles
     double* tab_zero = nullptr;             // one all-zero table row (stored-E mode)
-    int diag_otf = -1;                      // option "diag_on_the_fly": -1 auto (from 26 local qubits), 0 stored E, 1 on the fly
+    int diag_otf = -1;                      // option "diag_on_the_fly": -1 auto (from 25 local qubits), 0 stored E, 1 on the fly
     // options
     double tol = 1e-14, theta_max = 3.0;
     int max_terms = 64, fixed_terms = 0, force_flat = 0;
@@ -255,13 +255,18 @@ static WsPlan make_ws_plan_tb(int nl, int sb_bits, int tb) {
 // is best while that holds (N_local <= 27); larger blocks want a shorter lead to stay inside L2.
 // Up to 21 local qubits the whole shard is ONE super-block (a single fused launch, measured faster:
 // 19/20/21 qubits 22/31/51 us against 28/39/63 us with a plain launch on top).
-static int auto_sb_bits(int nl) { return nl <= 21 ? nl : std::max(18, std::min(21, nl - 9)); }
-// 2^21-amplitude blocks (30 local qubits) hold 64 MiB of x + y each: with any lead two of them are in flight and the
-// second sub-pass re-reads x and y from HBM (ncu: 80.5 instead of 40 B/amp); lead 0 hands out B(s) right after A(s).
-static int auto_sb_lag(int sbits) { return sbits <= 18 ? 3 : (sbits == 19 ? 2 : (sbits == 20 ? 1 : 0)); }
+// With the diagonal evaluated on the fly no E stream passes through the L2 and larger blocks stay resident; measured
+// (same box, tools/ab_opts.py, profiles/r02_ab_sb_*.txt): 25 q 2^19 / lead 2: -4 %; 27 q 2^19 / 2: -15 %; 28 q 2^20 / 1:
+// -14 %; 29 q 2^21 / 1: -7 % (sweep step -12 %); 30 q 2^21 with no lead (one 64 MiB block in flight instead of two): -4 %.
+static int auto_sb_bits(int nl, bool otf) {
+    if (nl <= 21) return nl;
+    if (!otf) return std::max(18, std::min(21, nl - 9));
+    return nl <= 24 ? 18 : (nl <= 27 ? 19 : (nl == 28 ? 20 : 21));
+}
+static int auto_sb_lag(int sbits, int nl) { return sbits <= 18 ? 3 : (sbits == 19 ? 2 : ((sbits == 21 && nl >= 30) ? 0 : 1)); }
 
-static WsPlan make_ws_plan(int nl, int sb_bits, int tile_bits) {
-    if (sb_bits == 0) sb_bits = auto_sb_bits(nl);
+static WsPlan make_ws_plan(int nl, int sb_bits, int tile_bits, bool otf = true) {
+    if (sb_bits == 0) sb_bits = auto_sb_bits(nl, otf);
     if (tile_bits == 11 || tile_bits == 12) return make_ws_plan_tb(nl, sb_bits, tile_bits);
     const WsPlan a = make_ws_plan_tb(nl, sb_bits, 11), b = make_ws_plan_tb(nl, sb_bits, 12);
     return (a.n_plain <= b.n_plain) ? a : b;
@@ -347,9 +352,9 @@ static HParams hparams_from_sites(const qsb_ctx* c, const double* hw_site, const
     h.chan[1] = amp;
     h.chan[2] = det;
     // diagonal model: detuning, plus (on the fly) the static 1- / 2-local part with this rank's bits folded in
-    // measured (same box, tools/ab_hpsi.py): on the fly is 1.3 % slower at 25 qubits, 2.8 % (H psi) / 4.7 % (sweep step)
-    // faster at 28, where the E stream competes with two state-sized streams per pass
-    h.otf = c->dm_ok && (c->diag_otf < 0 ? c->nl >= 26 : c->diag_otf != 0);
+    // measured (same box): with the same plan on the fly is 1.3 % slower at 25 qubits and 2.8 % faster at 28; but without
+    // an E stream through the L2 a larger super-block stays resident (auto_sb_bits), which wins 4 % at 25 and 14 % at 28
+    h.otf = c->dm_ok && (c->diag_otf < 0 ? c->nl >= 25 : c->diag_otf != 0);
     memset(h.lin, 0, sizeof(h.lin));
     h.c0 = -h.sp.d_rank;
     for (int b = 0; b < c->nl; ++b) h.lin[b] = -h.sp.dl[b];
@@ -411,7 +416,7 @@ static unsigned int take_tickets(qsb_ctx* c, int counter, u64 total, int grid) {
 static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, const HParams& hp, bool fuse, double2 scale,
                           int acc_mode, int red_mode, double* red_slot, const double2* const* peers) {
     // partner stages and their FIRST stage must be consumed by the same threads: one consumer group
-    const WsPlan w = make_ws_plan(c->nl, c->sb_bits, c->nranks > 1 ? 12 : c->ws_tile_bits);
+    const WsPlan w = make_ws_plan(c->nl, c->sb_bits, c->nranks > 1 ? 12 : c->ws_tile_bits, hp.otf);
     const u64 n_tiles = c->dim >> w.tb;
     const int grid = (int)std::min<u64>(n_tiles, (u64)c->n_sm);
     HpsiWs a{};
@@ -507,7 +512,7 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, const HParam
         a.hb = g.hb;
         a.hb0 = g.hb0;
         a.last = (last && fuse) ? 1 : 0;
-        a.lag = c->sb_lag > 0 ? c->sb_lag : (c->sb_lag < 0 ? 0 : auto_sb_lag(w.sbits));
+        a.lag = c->sb_lag > 0 ? c->sb_lag : (c->sb_lag < 0 ? 0 : auto_sb_lag(w.sbits, c->nl));
         // partner stages of this launch
         if (i == 0) {
             a.n_peer = (split == 2) ? 0 : np;
