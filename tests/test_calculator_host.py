@@ -208,3 +208,94 @@ def test_bitstring_helpers(fake):
     assert sum(counts.values()) == 500 and all(len(b) == 4 for b in counts)
     calc.close()
     assert calc._engine is None
+
+
+# ---- generalised Hamiltonians through the plugin surface, fake engine ----------------
+class GeneralFakeEngine(FakeEngine):
+    """FakeEngine + the per-site / operator-term entry points, arithmetic by the oracle's general propagator."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.w_amp = np.ones(self.n)
+        self.w_det = np.ones(self.n)
+        self.terms = []
+
+    def set_site_weights(self, w_omega=None, w_delta=None):
+        self.w_amp = np.ones(self.n) if w_omega is None else np.asarray(w_omega, float)
+        self.w_det = np.ones(self.n) if w_delta is None else np.asarray(w_delta, float)
+
+    def set_operator_terms(self, terms):
+        self.terms = list(terms)
+
+    def _h(self, a, d):
+        chan = {0: 1.0, 1: a, 2: d}
+        terms = []
+        for coef, x, y, z, nm, ch in self.terms:
+            ops = []
+            for name, m in zip("XYZN", (x, y, z, nm)):
+                ops += [(name, self.n - 1 - b) for b in range(self.n) if (m >> b) & 1]
+            terms.append((coef * chan[ch], ops))
+        return dict(e_int=self.e, hw_sites=0.5 * a * self.w_amp, d_sites=d * self.w_det, terms=terms)
+
+    def evolve_schedule(self, omega, delta, dt, eops=None):
+        for a, d, t in zip(omega, delta, dt):
+            self.psi = orc.general_propagate(self.psi, self.n, t, **self._h(a, d))
+            self.hpsi += 1
+        return None
+
+    def apply_h_to(self, psi, omega, delta):
+        return orc.general_apply(np.asarray(psi, complex).reshape(-1), self.n, **self._h(omega, delta))
+
+
+@pytest.fixture()
+def general_fake(monkeypatch):
+    monkeypatch.setattr(lib, "is_available", lambda: (True, ""))
+    monkeypatch.setattr(lib, "Engine", GeneralFakeEngine)
+    monkeypatch.setattr(lib, "pinned_empty", lambda n, dtype=np.complex128: np.empty(n, dtype=dtype))
+    return GeneralFakeEngine
+
+
+def test_site_weights_and_operator_hamiltonians_reach_the_engine(general_fake):
+    qbits, amp, det = _setup(4)
+    n = qbits.nqbits
+    w, v = np.array([1.0, 0.5, 2.0, 1.5]), np.array([0.0, 1.0, 1.0, -1.0])
+    h_static = qb.Operators([qb.Operator(["Z", "Z"], [0, 1], n, coef=0.3), qb.Operator("Y", 2, n, coef=0.1)])
+    h_amp = qb.Operators([qb.Operator(["X", "X"], [1, 3], n, coef=0.2)])
+    calc = qb.B200(qbits, amp, det, site_amplitude=w, site_detuning=v, hamiltonian=h_static, hamiltonian_amplitude=h_amp)
+    out = calc.calculate()
+    eng = calc._engine
+    assert np.array_equal(eng.w_amp, w) and np.array_equal(eng.w_det, v)
+    assert [t[-1] for t in eng.terms] == [0, 0, 1]  # channels: static, static, x amplitude
+    assert eng.terms[0][:5] == (0.3, 0, 0, 0b1100, 0) and eng.terms[1][:5] == (0.1, 0, 0b0010, 0, 0)
+    assert eng.terms[2][:5] == (0.2, 0b0101, 0, 0, 0)
+    # independent evaluation of the same schedule
+    e = orc.diagonal_energies(orc.interaction_matrix(qbits.positions), n)
+    psi = np.zeros(1 << n, complex)
+    psi[0] = 1.0
+    for a, d in zip(amp.values, det.values):
+        terms = orc.operators_as_terms(h_static) + orc.operators_as_terms(h_amp * float(a))
+        psi = orc.general_propagate(psi, n, 0.01, e_int=e, hw_sites=0.5 * a * w, d_sites=d * v, terms=terms)
+    assert np.max(np.abs(out["state"].reshape(-1) - psi)) < 1e-12
+    # Hamiltonian.apply goes through apply_h_to and leaves the evolved state alone
+    before = calc.statevector.copy()
+    y = calc.get_hamiltonian(2.0, 1.0).apply(np.eye(1 << n)[3])
+    assert y.shape == (1 << n,) and np.array_equal(eng.psi, before)
+    # a changed Hamiltonian rebuilds the context (the reference goes stale)
+    calc.hamiltonian = None
+    calc.calculate()
+    assert calc._engine is not eng and eng.closed and len(calc._engine.terms) == 1
+    calc.close()
+    with pytest.raises(Exception, match="one weight per qubit"):
+        qb.B200(qbits, amp, det, site_amplitude=[1.0, 2.0]).calculate()
+    with pytest.raises(Exception, match="number of qubits"):
+        qb.B200(qbits, amp, det, hamiltonian=qb.Operators([qb.Operator("X", 0, n + 1)])).calculate()
+
+
+def test_interaction_false_and_shard_return(general_fake):
+    qbits, amp, det = _setup(3)
+    calc = qb.B200(qbits, amp, det, interaction=False, return_state="shard")
+    out = calc.calculate()
+    assert np.all(calc._engine.e == 0.0)
+    assert out["state"].shape == (16, 1)  # one rank: the shard is the whole state
+    assert np.array_equal(out["state"].reshape(-1), calc.local_statevector)
+    calc.close()
