@@ -18,6 +18,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
+    config.addinivalue_line("markers", "timeout: per-test time limit (pytest-timeout)")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -28,6 +29,12 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         have_gpu = False
     if have_gpu:
+        # a hung kernel must be a failure with a stack trace, not a lost box: every GPU test gets a
+        # timeout (pytest-timeout, thread method: a blocked ctypes call cannot be interrupted by a signal)
+        if config.pluginmanager.hasplugin("timeout"):
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(1200 if "sharded" in item.name else 300, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:
