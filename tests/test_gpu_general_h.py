@@ -189,3 +189,27 @@ def test_tiled_spins_match_the_per_qubit_path_and_the_oracle(n):
     assert launches_plain >= 4 * n  # what the tile passes replace
     if n <= 17:
         assert np.max(np.abs(tiled - orc.get_spins(psi, n))) <= 1e-12
+
+
+@pytest.mark.parametrize("n", [8, 13])
+def test_per_site_schedule_rows(n):
+    """qsb_evolve_schedule_sites: every step carries its own Omega_q, delta_q per site (n_steps x N rows) -- the fully
+    general form of the README Hamiltonian's time dependence.  8 qubits: single-launch schedule kernel; 13: tiled."""
+    reg = qb.lattices.random_register(n, 0.9 * qb.blockade_radius(OMEGA_MAX), seed=60 + n)
+    rng = np.random.default_rng(n)
+    steps = 5
+    om = rng.uniform(0.5, OMEGA_MAX, size=(steps, n))
+    de = rng.uniform(-OMEGA_MAX, OMEGA_MAX, size=(steps, n))
+    dt = np.full(steps, 0.004)
+    e = orc.diagonal_energies(orc.interaction_matrix(reg.positions), n)
+    with lib.Engine(n) as eng:
+        eng.set_interaction(qb.interaction_matrix(reg.positions))
+        eng.reset_state()
+        eng.evolve_schedule_sites(om, de, dt)
+        got = eng.get_state()
+    psi = np.zeros(1 << n, complex)
+    psi[0] = 1.0
+    for s in range(steps):
+        psi = orc.general_propagate(psi, n, dt[s], e_int=e, hw_sites=0.5 * om[s], d_sites=de[s])
+    assert orc.infidelity(got, psi) <= 1e-10
+    assert np.max(np.abs(got - psi)) <= 1e-9
