@@ -41,3 +41,13 @@ def test_clock_sampler_degrades_without_nvml():
     s.start()
     out = s.stop()
     assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples"}
+
+
+def test_both_arms_describe_the_same_config():
+    """The driver compares the `config` objects of the two arms: they come from one function."""
+    import bench
+
+    for n, world in ((25, 1), (26, 2), (28, 8)):
+        a, b = bench.make_config(n, world), bench.make_config(n, world)
+        assert a == b and a["qubits"] == n and a["amplitudes_per_gpu"] == 1 << 25
+        assert set(a) == {"workload", "qubits", "amplitudes_per_gpu", "l2", "parallelism", "stepper"}
