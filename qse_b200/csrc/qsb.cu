@@ -263,7 +263,11 @@ static int auto_sb_bits(int nl, bool otf) {
     if (!otf) return std::max(18, std::min(21, nl - 9));
     return nl <= 24 ? 18 : (nl <= 27 ? 19 : (nl == 28 ? 20 : 21));
 }
-static int auto_sb_lag(int sbits, int nl) { return sbits <= 18 ? 3 : (sbits == 19 ? 2 : ((sbits == 21 && nl >= 30) ? 0 : 1)); }
+// (no lead only on one GPU: sharded, 30 local qubits are NVLink-bound and the lead-1 schedule is the one validated
+// at 33 qubits on 8 GPUs)
+static int auto_sb_lag(int sbits, int nl, int nranks) {
+    return sbits <= 18 ? 3 : (sbits == 19 ? 2 : ((sbits == 21 && nl >= 30 && nranks == 1) ? 0 : 1));
+}
 
 static WsPlan make_ws_plan(int nl, int sb_bits, int tile_bits, bool otf = true) {
     if (sb_bits == 0) sb_bits = auto_sb_bits(nl, otf);
@@ -512,7 +516,7 @@ static int launch_hpsi_ws(qsb_ctx* c, const double2* x, double2* y, const HParam
         a.hb = g.hb;
         a.hb0 = g.hb0;
         a.last = (last && fuse) ? 1 : 0;
-        a.lag = c->sb_lag > 0 ? c->sb_lag : (c->sb_lag < 0 ? 0 : auto_sb_lag(w.sbits, c->nl));
+        a.lag = c->sb_lag > 0 ? c->sb_lag : (c->sb_lag < 0 ? 0 : auto_sb_lag(w.sbits, c->nl, c->nranks));
         // partner stages of this launch
         if (i == 0) {
             a.n_peer = (split == 2) ? 0 : np;
